@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- MSDeformAttn forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload a2d|ytvos|decoder] [--regime init|uniform] [--dtype f32|bf16]
+
+A *step* is one pass of the hot path -- MSDeformAttnFunction forward + backward (grad_value,
+grad_sampling_loc, grad_attn_weight) -- over one batch of synthetic input.  At N=1 the batch is
+BASELINE.json configs[1]: the A2D ResNet-101 encoder shape (5 frames, 360x640 -> levels 45x80, 23x40,
+12x20, 6x10; S = Lq = 4820; M=8, D=32, L=4, P=4), fp32.  With N GPUs every rank runs that batch on its
+own shard of frames (weak scaling, no collective on the op -- SURVEY.md section 8e).
+
+One JSON line is printed by rank 0:
+  value         queries/s (a query = one (n, q) pair, all heads), whole job, inputs resident in HBM,
+                device-timed with CUDA events over exactly K steps, max over ranks.  Steps cycle through
+                `input_sets` distinct input sets (> L2 in total) so no step finds its inputs in L2.
+  e2e           the same metric through the public API with HOST buffers: pinned-host -> device copies of
+                value / sampling_locations / attention_weights / grad_output, forward, backward, and
+                device -> host copies of output and the three gradients, all inside the timed region.
+  roofline      for the dominant kernel (the backward): algorithmic bytes per launch / its mean launch
+                duration (CUDA events around each launch) vs the measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline  the reference's CPU path (grid_sample formulation, oracle/grid_sample_port.py) timed on
+                this box's host cores, rank 0, N=1 only.
+`--impl reference` times only that CPU path (all host threads), same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "msdeformattn_fwd_bwd_queries_per_sec"
+UNIT = "queries/s"
+HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="a2d", choices=["a2d", "ytvos", "decoder"])
+    ap.add_argument("--regime", default="init", choices=["init", "uniform"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--input-sets", type=int, default=6)
+    ap.add_argument("--no-graph", action="store_true", help="launch from Python instead of CUDA graphs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget for the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def pick_workload(name):
+    from ocpg_b200 import workloads as W
+    return {"a2d": W.A2D_ENCODER, "ytvos": W.YTVOS_ENCODER, "decoder": W.A2D_DECODER}[name]
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference path (oracle/ -- the one place bench.py may execute it)
+# ----------------------------------------------------------------------------------------------
+def time_cpu_reference(wl, regime, steps, warmup, budget_s):
+    """grid_sample formulation of the reference (ms_deform_attn_func.py:41-61), forward + autograd
+    backward, fp32, all host threads.  Each step is a bounded sample of the workload: as many of its
+    frames as fit the time budget."""
+    import dataclasses
+    import torch
+    from ocpg_b200.workloads import make_inputs
+    from oracle.grid_sample_port import msda_grid_sample_fwd_bwd
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = make_inputs(wl, regime, seed=0, device="cpu")
+
+    def run(nf):
+        msda_grid_sample_fwd_bwd(x["value"][:nf], x["shapes"], x["loc"][:nf], x["attn"][:nf], x["grad_out"][:nf])
+
+    t0 = time.perf_counter(); run(1); t1 = time.perf_counter() - t0        # first call: page-in, 1 frame
+    t0 = time.perf_counter(); run(1); t1 = min(t1, time.perf_counter() - t0)
+    per_frame = t1
+    nf = wl.n_frames
+    while nf > 1 and per_frame * nf * (steps + warmup) > budget_s:
+        nf -= 1
+    for _ in range(warmup):
+        run(nf)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run(nf)
+    dt = time.perf_counter() - t0
+    q = nf * wl.n_queries * steps
+    return {"value": q / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nf} of {wl.n_frames} frames per step x {steps} steps (+{warmup} warm-up), fwd+bwd fp32, "
+                      f"grid_sample formulation, {torch.get_num_threads()} threads",
+            "ms_per_step": dt / steps * 1e3, "frames_per_step": nf}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    wl = pick_workload(args.workload)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # keep the whole run within a few minutes whatever K and W are
+    r = time_cpu_reference(wl, args.regime, steps, warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "regime": args.regime, "frames_per_step": r["frames_per_step"],
+                   "levels": [list(l) for l in wl.levels], "Lq": wl.n_queries, "M": wl.n_heads, "D": wl.head_dim,
+                   "L": wl.L, "P": wl.n_points},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import ocpg_b200
+    from ocpg_b200 import dist as D
+    from ocpg_b200 import MultiScaleDeformableAttention as MSDA
+    from ocpg_b200.workloads import make_inputs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    rank, local_rank, world = D.init("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ocpg_b200.lib()                                                   # fail loudly if the extension is missing
+    wl = pick_workload(args.workload)
+    vdt = torch.bfloat16 if args.dtype == "bf16" else None
+    vbytes = 2 if args.dtype == "bf16" else 4
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+    R = max(1, args.input_sets)
+
+    # R distinct input sets; each rank owns its own shard of frames (seeded by rank): weak scaling
+    sets = [make_inputs(wl, args.regime, seed=1000 * rank + i, device=dev, value_dtype=vdt) for i in range(R)]
+    fwd_bytes, bwd_bytes = wl.algorithmic_bytes(vbytes, vbytes)
+    set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
+
+    def step(x):
+        out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
+        grads = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["grad_out"], 64)
+        return out, grads
+
+    # one CUDA graph per input set (forward kernel, grad_value memset, backward kernel)
+    graphs = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for x in sets:
+                step(x)
+        torch.cuda.synchronize()
+        graphs, keep = [], []
+        for x in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keep.append(step(x))
+            graphs.append(g)
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % R].replay()
+        else:
+            step(sets[i % R])
+
+    for i in range(Wm):
+        run_step(i)
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, barrier + sync on both sides, device-timed, max over ranks
+    n0 = ocpg_b200.launch_count()
+    clocks = ClockSampler(local_rank)
+    D.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        run_step(i)
+    e1.record()
+    torch.cuda.synchronize(); D.barrier()
+    ms_total = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    clk = clocks.stop()
+    launches = (2 * K) if graphs is not None else (ocpg_b200.launch_count() - n0)
+    ms_per_step = ms_total / K
+    value_qps = wl.queries * world / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations (events around each launch, same rotating inputs)
+    def time_kernel(fn, iters):
+        evs = []
+        for i in range(iters):
+            x = sets[i % R]
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(x); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in evs]
+        return statistics.mean(ts), min(ts)
+
+    iters = min(K, 60)
+    fwd_ms, fwd_min = time_kernel(lambda x: MSDA.ms_deform_attn_forward(
+        x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64), iters)
+    bwd_ms, bwd_min = time_kernel(lambda x: MSDA.ms_deform_attn_backward(
+        x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["grad_out"], 64), iters)
+    peak, peak_src = hbm_peak()
+    bwd_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = fwd_bytes / (fwd_ms * 1e-3) / 1e9
+    step_gbs = (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers in, host buffers out, through the autograd operator
+    e2e = None
+    if not args.no_e2e:
+        from ocpg_b200 import MSDeformAttnFunction
+        hx = {k: sets[0][k].cpu().pin_memory() for k in ("value", "loc", "attn", "grad_out")}
+        h2d = sum(t.numel() * t.element_size() for t in hx.values())
+        x0 = sets[0]
+        outs_shape = [(x0["grad_out"].shape, x0["grad_out"].dtype), (x0["value"].shape, x0["value"].dtype),
+                      (x0["loc"].shape, x0["loc"].dtype), (x0["attn"].shape, x0["attn"].dtype)]
+        hout = [torch.empty(s, dtype=dt).pin_memory() for s, dt in outs_shape]
+        d2h = sum(t.numel() * t.element_size() for t in hout)
+
+        def e2e_step():
+            v = hx["value"].to(dev, non_blocking=True).requires_grad_(True)
+            s = hx["loc"].to(dev, non_blocking=True).requires_grad_(True)
+            a = hx["attn"].to(dev, non_blocking=True).requires_grad_(True)
+            go = hx["grad_out"].to(dev, non_blocking=True)
+            out = MSDeformAttnFunction.apply(v, x0["shapes"], x0["start"], s, a, 64)
+            out.backward(go)
+            for h, d in zip(hout, (out.detach(), v.grad, s.grad, a.grad)):
+                h.copy_(d, non_blocking=True)
+
+        Ke = min(K, 20)
+        for _ in range(3):
+            e2e_step()
+        D.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(Ke):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        D.barrier()
+        e2e_ms = D.max_over_ranks(max(a.elapsed_time(b), wall_ms), dev) / Ke
+        e2e = {"value": wl.queries * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": Ke}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = time_cpu_reference(wl, args.regime, steps=3, warmup=1, budget_s=args.cpu_seconds)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value_qps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": wl.name, "regime": args.regime, "frames_per_gpu": wl.n_frames,
+                       "levels": [list(l) for l in wl.levels], "Lq": wl.n_queries, "M": wl.n_heads, "D": wl.head_dim,
+                       "L": wl.L, "P": wl.n_points, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "l2_policy": f"steps cycle through {R} distinct input sets of {set_bytes / 1e6:.0f} MB "
+                                    f"(+ as much output) each: inputs larger than L2 between reuses",
+                       "launch": "python" if graphs is None else "cuda-graph per step (fwd kernel, memset, bwd kernel)"},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "msda_bwd_tiled", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": bwd_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": bwd_bytes, "launch_ms": bwd_ms, "launch_ms_min": bwd_min},
+            "roofline_fwd": {"kernel": "msda_fwd_tiled", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
+                             "algorithmic_bytes": fwd_bytes, "launch_ms": fwd_ms, "launch_ms_min": fwd_min},
+            "roofline_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes": fwd_bytes + bwd_bytes},
+            "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    D.finalize()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,122 @@
+/*
+ * msda_sm100.h -- C ABI of libmsda_sm100.so: multi-scale deformable attention (MSDeformAttn)
+ * forward and backward for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's native component models/ops/src/**.  Each entry
+ * point replaces one reference launch wrapper and keeps its argument list (plain device pointers and
+ * sizes, the caller's stream); no torch/ATen type appears here:
+ *
+ *   msda_forward_*   <->  ms_deformable_im2col_cuda(stream, value, shapes, start, loc, attn,
+ *                           batch, S, M, D, L, Lq, P, out)          ms_deform_im2col_cuda.cuh:923-937
+ *                         as driven by ms_deform_attn_cuda_forward  ms_deform_attn_cuda.cu:20-80
+ *   msda_backward_*  <->  ms_deformable_col2im_cuda(stream, grad_col, value, shapes, start, loc,
+ *                           attn, batch, S, M, D, L, Lq, P, grad_value, grad_loc, grad_attn)
+ *                                                                   ms_deform_im2col_cuda.cuh:956-973
+ *                         as driven by ms_deform_attn_cuda_backward ms_deform_attn_cuda.cu:83-153
+ *
+ * The Python-visible functions the reference exports through pybind11 (vision.cpp:13-16,
+ * ms_deform_attn.h:36-77) -- ms_deform_attn_forward / ms_deform_attn_backward -- are rebuilt on top
+ * of this ABI with ctypes in ocpg_b200/MultiScaleDeformableAttention.py; INTEGRATION.md shows the
+ * binding.
+ *
+ * Layouts (row-major, contiguous, device memory):
+ *   value            [batch][spatial_size][num_heads][channels]
+ *   spatial_shapes   [num_levels][2]   int64, (H_l, W_l)        -- read on the device, like the reference
+ *   level_start_index[num_levels]      int64
+ *   sampling_loc     [batch][num_query][num_heads][num_levels][num_point][2]   (x, y) in [0,1]
+ *   attn_weight      [batch][num_query][num_heads][num_levels][num_point]
+ *   output, grad_output [batch][num_query][num_heads*channels]
+ *
+ * Differences from the reference wrappers (all strict supersets):
+ *   - one launch for any batch: there is no im2col_step chunk loop, hence no batch % im2col_step rule;
+ *   - the batch term of every offset is 64-bit (the reference's int overflows beyond 2^31 elements);
+ *   - msda_backward_* zero-fills grad_value itself (the reference's caller does, cu:121) and writes
+ *     every element of grad_sampling_loc / grad_attn_weight (no zero-fill needed);
+ *   - launch errors are returned, not printf'd (cuh:948-952).
+ *
+ * Every function is stateless, re-entrant and stream-ordered: it enqueues work on `stream` and
+ * returns without synchronising; it allocates nothing and keeps no device state.
+ * Return value: 0 on success, a cudaError_t value (> 0) if a CUDA call failed, or a negative
+ * MSDA_ERR_* code for an argument error; msda_last_error() gives the message for this thread.
+ */
+#ifndef MSDA_SM100_H_
+#define MSDA_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+#define MSDA_OK 0
+#define MSDA_ERR_INVALID_ARGUMENT (-1) /* null pointer, non-positive dimension, misaligned pointer */
+#define MSDA_ERR_UNSUPPORTED (-2)      /* shape outside what the kernels cover (see msda_kernel_plan) */
+
+/* Opaque cudaStream_t (CUstream); 0 / NULL is the legacy default stream. */
+typedef void *msda_stream_t;
+
+int msda_abi_version(void);
+const char *msda_last_error(void);
+
+/* ---- fp32 (the reference's production dtype; deformable_transformer.py:250 disables autocast) ---- */
+int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const float *sampling_loc, const float *attn_weight,
+                     int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                     int num_query, int num_point, float *output, msda_stream_t stream);
+
+int msda_backward_f32(const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const float *sampling_loc, const float *attn_weight,
+                      int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point,
+                      float *grad_value, float *grad_sampling_loc, float *grad_attn_weight,
+                      msda_stream_t stream);
+
+/* ---- fp64 (the reference dispatches float and double, cu:64; its tests run in double) ---- */
+int msda_forward_f64(const double *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const double *sampling_loc, const double *attn_weight,
+                     int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                     int num_query, int num_point, double *output, msda_stream_t stream);
+
+int msda_backward_f64(const double *grad_output, const double *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const double *sampling_loc, const double *attn_weight,
+                      int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point,
+                      double *grad_value, double *grad_sampling_loc, double *grad_attn_weight,
+                      msda_stream_t stream);
+
+/* ---- bf16 value (new; value / output / grad_output are bf16 bit patterns, loc and attn stay fp32,
+ *      accumulation is fp32).  grad_value is accumulated in the fp32 buffer grad_value_f32
+ *      (same shape as value, zero-filled by the call); if grad_value_bf16 is non-NULL the rounded
+ *      result is also written there. ---- */
+int msda_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *sampling_loc, const float *attn_weight,
+                      int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, uint16_t *output, msda_stream_t stream);
+
+int msda_backward_bf16(const uint16_t *grad_output, const uint16_t *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const float *sampling_loc, const float *attn_weight,
+                       int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                       int num_query, int num_point,
+                       float *grad_value_f32, uint16_t *grad_value_bf16,
+                       float *grad_sampling_loc, float *grad_attn_weight, msda_stream_t stream);
+
+/* Which kernel a call with these dimensions runs: 1 = the sm_100a tiled kernel (channels == 32,
+ * num_levels <= 16, num_levels*num_point <= 32), 0 = the generic kernel (any shape).  For tests and
+ * benchmarks; `elem_bytes` is 2, 4 or 8. */
+int msda_kernel_plan(int elem_bytes, int num_heads, int channels, int num_levels, int num_point);
+
+/* Number of kernel launches (memsets excluded) the library has enqueued from this process so far;
+ * used by bench.py to report `gpu_launches`. */
+uint64_t msda_launch_count(void);
+
+/* Tuning knobs for experiments (not needed for normal use).  Known keys: "fwd_ctas_per_sm",
+ * "bwd_ctas_per_sm", "force_generic", "force_linear_walk", "debug_skip_scatter" (the last one makes
+ * grad_value wrong on purpose: it exists to measure the cost of the scatter).  Returns 0, or MSDA_ERR_INVALID_ARGUMENT for an unknown key. */
+int msda_set_option(const char *key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_SM100_H_ */

@@ -1,0 +1,16 @@
+"""ocpg_b200 -- B200-native (sm_100a) multi-scale deformable attention for TJUMMG/OCPG.
+
+A drop-in for the reference's ``models/ops`` package and nothing else:
+
+    from ocpg_b200 import MSDeformAttn, MSDeformAttnFunction          # same API as models.ops.{modules,functions}
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA            # same functions as the pybind11 module
+
+Python/PyTorch host code calls hand-written CUDA kernels through the C ABI of include/msda_sm100.h
+(ctypes); no Triton, no multi-backend dispatch, no CPU fallback.
+"""
+from ._lib import build, lib, launch_count, set_option, LIB_PATH  # noqa: F401
+from .functions import MSDeformAttnFunction  # noqa: F401
+from .modules import MSDeformAttn  # noqa: F401
+from . import MultiScaleDeformableAttention  # noqa: F401
+
+__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MultiScaleDeformableAttention", "build", "lib"]

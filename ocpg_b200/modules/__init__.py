@@ -1,0 +1,1 @@
+from .ms_deform_attn import MSDeformAttn  # noqa: F401

@@ -1,0 +1,122 @@
+"""``MSDeformAttn`` nn.Module -- drop-in for the reference's models/ops/modules/ms_deform_attn.py:31-118.
+
+Same constructor ``(d_model=256, n_levels=4, n_heads=8, n_points=4)``, same parameters and
+state_dict keys (``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj``, each
+``.weight`` / ``.bias``; :57-60) so reference checkpoints load unchanged, same initialisation (:62-78),
+same ``forward`` signature and the same **3-tuple** return
+``(output, sampling_locations, attention_weights)`` (:118 -- OCPG's decoder consumes the last two,
+deformable_transformer.py:365-375).
+
+Host-side differences:
+  * the sampling op is ocpg_b200's sm_100a kernels (through MSDeformAttnFunction);
+  * the ``sum(H*W) == Len_in`` check (:94), which costs the reference one device->host sync per call, is
+    done once per distinct ``input_spatial_shapes`` tensor and cached.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..functions import MSDeformAttnFunction
+
+
+def _is_power_of_2(n):
+    if not isinstance(n, int) or n < 0:
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return n != 0 and (n & (n - 1)) == 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        """Multi-scale deformable attention.
+
+        :param d_model   hidden dimension
+        :param n_levels  number of feature levels
+        :param n_heads   number of attention heads
+        :param n_points  number of sampling points per attention head per feature level
+        """
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        if not _is_power_of_2(d_model // n_heads):
+            warnings.warn("You'd better set d_model in MSDeformAttn to make the dimension of each attention head a "
+                          "power of 2 which is more efficient in our CUDA implementation.")
+        self.im2col_step = 64          # kept for API parity (reference :49); the kernels ignore it
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._shape_ok = {}            # (data_ptr, version, Len_in) of spatial_shapes tensors already verified
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """Reference :62-78: zero offset weights, offset bias = one of n_heads compass directions
+        (max-norm 1) scaled by the point index 1..n_points; zero attention logits; Xavier projections."""
+        nn.init.constant_(self.sampling_offsets.weight.data, 0.0)
+        angle = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        direction = torch.stack([angle.cos(), angle.sin()], -1)
+        direction = direction / direction.abs().max(-1, keepdim=True)[0]
+        grid = direction.view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
+        grid = grid * torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid.reshape(-1))
+        nn.init.constant_(self.attention_weights.weight.data, 0.0)
+        nn.init.constant_(self.attention_weights.bias.data, 0.0)
+        nn.init.xavier_uniform_(self.value_proj.weight.data)
+        nn.init.constant_(self.value_proj.bias.data, 0.0)
+        nn.init.xavier_uniform_(self.output_proj.weight.data)
+        nn.init.constant_(self.output_proj.bias.data, 0.0)
+
+    def _check_shapes(self, spatial_shapes, len_in):
+        key = (spatial_shapes.data_ptr(), spatial_shapes._version, int(len_in))
+        if key not in self._shape_ok:
+            total = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())      # one sync, then cached
+            assert total == len_in, f"sum(H*W)={total} != Len_in={len_in}"       # reference :94
+            if len(self._shape_ok) > 64:
+                self._shape_ok.clear()
+            self._shape_ok[key] = True
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """
+        :param query                    (N, Length_query, C)
+        :param reference_points         (N, Length_query, n_levels, 2) in [0, 1], top-left (0,0), bottom-right (1,1),
+                                        including padding area; or (N, Length_query, n_levels, 4) = boxes (cx, cy, w, h)
+        :param input_flatten            (N, sum_l H_l*W_l, C)
+        :param input_spatial_shapes     (n_levels, 2) [(H_0, W_0), ...]
+        :param input_level_start_index  (n_levels,)
+        :param input_padding_mask       (N, sum_l H_l*W_l), True for padding elements
+
+        :return (output (N, Length_query, C), sampling_locations (N, Lq, M, L, P, 2), attention_weights (N, Lq, M, L, P))
+        """
+        N, Len_q, _ = query.shape
+        N, Len_in, _ = input_flatten.shape
+        self._check_shapes(input_spatial_shapes, Len_in)
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+
+        value = self.value_proj(input_flatten)                                           # :96
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))           # :97-98
+        value = value.view(N, Len_in, M, self.d_model // M)
+        offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)                # :100
+        weights = F.softmax(self.attention_weights(query).view(N, Len_q, M, L * P), -1)  # :101-102
+        weights = weights.view(N, Len_q, M, L, P)
+        if reference_points.shape[-1] == 2:                                              # :104-107
+            wh = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
+            sampling_locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:                                            # :108-110
+            sampling_locations = reference_points[:, :, None, :, None, :2] \
+                + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5
+        else:
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
+                reference_points.shape[-1]))
+        output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                            sampling_locations.contiguous(), weights.contiguous(), self.im2col_step)
+        output = self.output_proj(output)                                                # :116
+        return output, sampling_locations, weights                                       # :118

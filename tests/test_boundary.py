@@ -1,0 +1,148 @@
+"""CPU suite for the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, the Python mirror of the reference interface has the reference's names / signatures / error
+behaviour, and the product never touches oracle/.  No compute calls (no GPU here)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "msda_sm100.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(msda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    import ocpg_b200
+    from ocpg_b200 import _lib
+    ocpg_b200.build()
+    syms = header_symbols()
+    assert syms == sorted(_lib.SYMBOLS), (syms, sorted(_lib.SYMBOLS))
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(L, s), s
+    assert ocpg_b200.lib().msda_abi_version() == 1
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    from ocpg_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_kernel_plan():
+    import ocpg_b200
+    L = ocpg_b200.lib()
+    assert L.msda_kernel_plan(4, 8, 32, 4, 4) == 1       # production layout -> tiled sm_100a kernel
+    assert L.msda_kernel_plan(2, 8, 32, 4, 4) == 1
+    assert L.msda_kernel_plan(8, 8, 32, 4, 4) == 0       # fp64 -> generic
+    assert L.msda_kernel_plan(4, 8, 64, 4, 4) == 0
+    assert L.msda_kernel_plan(4, 8, 32, 4, 16) == 0
+
+
+def test_argument_errors_do_not_touch_the_gpu():
+    import ocpg_b200
+    L = ocpg_b200.lib()
+    rc = L.msda_forward_f32(None, None, None, None, None, 1, 0, 8, 32, 4, 1, 4, None, None)   # S = 0
+    assert rc == -1 and b"dimensions" in L.msda_last_error()
+    assert L.msda_set_option(b"no_such_key", 1) == -1
+    # empty batch / no queries: success without any pointer
+    assert L.msda_forward_f32(None, None, None, None, None, 0, 10, 8, 32, 4, 5, 4, None, None) == 0
+    assert L.msda_forward_f64(None, None, None, None, None, 2, 10, 8, 32, 4, 0, 4, None, None) == 0
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for base in ("ocpg_b200", "models"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
+                    txt = open(os.path.join(dp, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "oracle/_ref" in txt:
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_operator_api_matches_reference_names():
+    from ocpg_b200 import MSDeformAttnFunction, MSDeformAttn
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    # reference: functions/ms_deform_attn_func.py:23, :32 ; vision.cpp:14-15 ; modules/ms_deform_attn.py:32, :80
+    assert list(inspect.signature(MSDeformAttnFunction.forward).parameters) == [
+        "ctx", "value", "value_spatial_shapes", "value_level_start_index", "sampling_locations", "attention_weights",
+        "im2col_step"]
+    assert list(inspect.signature(MSDA.ms_deform_attn_forward).parameters) == [
+        "value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight", "im2col_step"]
+    assert list(inspect.signature(MSDA.ms_deform_attn_backward).parameters) == [
+        "value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight", "grad_output", "im2col_step"]
+    assert list(inspect.signature(MSDeformAttn.__init__).parameters) == ["self", "d_model", "n_levels", "n_heads", "n_points"]
+    assert list(inspect.signature(MSDeformAttn.forward).parameters) == [
+        "self", "query", "reference_points", "input_flatten", "input_spatial_shapes", "input_level_start_index",
+        "input_padding_mask"]
+
+
+def test_reference_import_paths_resolve():
+    from models.ops.modules import MSDeformAttn                     # deformable_transformer.py:20
+    from models.ops.functions import MSDeformAttnFunction           # modules/ms_deform_attn.py:22
+    import MultiScaleDeformableAttention as MSDA                    # functions/ms_deform_attn_func.py:18
+    import ocpg_b200
+    assert MSDeformAttn is ocpg_b200.MSDeformAttn and MSDeformAttnFunction is ocpg_b200.MSDeformAttnFunction
+    assert MSDA.ms_deform_attn_forward is ocpg_b200.MultiScaleDeformableAttention.ms_deform_attn_forward
+
+
+def test_cpu_tensors_raise_like_the_reference():
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    v = torch.zeros(1, 6, 2, 4)
+    shapes = torch.tensor([[2, 3]]); start = torch.tensor([0])
+    loc = torch.zeros(1, 3, 2, 1, 2, 2); attn = torch.zeros(1, 3, 2, 1, 2)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):       # ms_deform_attn.h:54
+        MSDA.ms_deform_attn_forward(v, shapes, start, loc, attn, 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDA.ms_deform_attn_backward(v, shapes, start, loc, attn, torch.zeros(1, 3, 8), 64)
+    with pytest.raises(RuntimeError, match="contiguous"):                       # cu:28
+        MSDA.ms_deform_attn_forward(v.transpose(1, 2), shapes, start, loc, attn, 64)
+
+
+def test_module_parameters_and_init_match_reference_scheme():
+    import math
+    from ocpg_b200 import MSDeformAttn
+    torch.manual_seed(0)
+    m = MSDeformAttn(256, 4, 8, 4)
+    sd = m.state_dict()
+    assert sorted(sd) == ["attention_weights.bias", "attention_weights.weight", "output_proj.bias", "output_proj.weight",
+                          "sampling_offsets.bias", "sampling_offsets.weight", "value_proj.bias", "value_proj.weight"]
+    assert sd["sampling_offsets.weight"].shape == (8 * 4 * 4 * 2, 256) and not sd["sampling_offsets.weight"].any()
+    assert sd["attention_weights.weight"].shape == (8 * 4 * 4, 256) and not sd["attention_weights.weight"].any()
+    assert not sd["attention_weights.bias"].any() and not sd["value_proj.bias"].any() and not sd["output_proj.bias"].any()
+    bias = sd["sampling_offsets.bias"].view(8, 4, 4, 2)
+    # reference ms_deform_attn.py:64-70: head h points along angle 2*pi*h/8 (max-norm 1), point i scaled by i+1
+    for h in range(8):
+        th = 2 * math.pi * h / 8
+        d = torch.tensor([math.cos(th), math.sin(th)])
+        d = d / d.abs().max()
+        for i in range(4):
+            assert torch.allclose(bias[h, :, i], (d * (i + 1)).expand(4, 2), atol=1e-6)
+    assert m.im2col_step == 64
+    with pytest.raises(ValueError):
+        MSDeformAttn(250, 4, 8, 4)
+
+
+def test_workload_shapes_and_bytes():
+    from ocpg_b200.workloads import A2D_ENCODER, YTVOS_ENCODER, A2D_DECODER, shard_frames
+    assert A2D_ENCODER.levels == ((45, 80), (23, 40), (12, 20), (6, 10)) and A2D_ENCODER.S == 4820
+    assert YTVOS_ENCODER.levels == ((80, 144), (40, 72), (20, 36), (10, 18)) and YTVOS_ENCODER.S == 15300
+    fwd, bwd = A2D_ENCODER.algorithmic_bytes()
+    assert fwd == 24100 * 3584 and bwd == 24100 * 6144            # 3584 / 6144 B per query
+    assert A2D_DECODER.queries == 25
+    covered = []
+    for r in range(3):
+        f, n = shard_frames(10, 3, r)
+        covered += list(range(f, f + n))
+    assert covered == list(range(10))

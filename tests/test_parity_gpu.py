@@ -1,0 +1,439 @@
+"""GPU parity suite (run on the B200 box: python -m pytest tests -m gpu).
+
+Every test calls the product through its public boundary (ocpg_b200.MultiScaleDeformableAttention ->
+ctypes -> libmsda_sm100.so, or MSDeformAttnFunction / MSDeformAttn on top of it) and compares with
+  * the committed golden vectors (generated from the reference's Python implementation),
+  * the CPU oracle (oracle/msda_oracle.c, fp64) on the same seeded inputs,
+  * the reference's own CUDA op rebuilt for sm_100a (oracle/_ref, when present),
+  * size-independent properties (adjoint identities, linearity, determinism) at BASELINE.json's full sizes.
+
+Tolerances (north_star): forward <= 1e-5, backward <= 1e-4, as max|a-b| / max|b| per tensor against the
+fp64 oracle fed the same fp32-valued inputs.  grad_sampling_loc is compared away from bilinear cell
+boundaries (oracle/compare.py::boundary_mask, eps = 1e-4 px), where it is discontinuous.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL, BWD_TOL = 1e-5, 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import ocpg_b200
+    ocpg_b200.lib()                      # fail loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def ours(x, dev, dtype=torch.float32, value_dtype=None):
+    """Run forward + backward through the C-ABI shim; returns numpy (out, gv, gl, ga)."""
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    vdt = value_dtype or dtype
+    t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))).to(dev, dt).contiguous()
+    v, go = t(x["value"], vdt), t(x["grad_out"], vdt)
+    loc, attn = t(x["loc"], dtype), t(x["attn"], dtype)
+    shapes, start = t(x["shapes"], torch.int64), t(x["start"], torch.int64)
+    out = MSDA.ms_deform_attn_forward(v, shapes, start, loc, attn, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, shapes, start, loc, attn, go, 64)
+    torch.cuda.synchronize()
+    f = lambda a: a.double().cpu().numpy()
+    return f(out), f(gv), f(gl), f(ga)
+
+
+def oracle64(x):
+    import oracle
+    n = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    a = {k: n(v) for k, v in x.items()}
+    out = oracle.c_forward(a["value"], a["shapes"], a["start"], a["loc"], a["attn"], np.float64)
+    gv, gl, ga = oracle.c_backward(a["value"], a["shapes"], a["start"], a["loc"], a["attn"], a["grad_out"], np.float64)
+    return out, gv, gl, ga
+
+
+def check(got, want, x, fwd_tol=FWD_TOL, bwd_tol=BWD_TOL, eps=1e-4):
+    from oracle.compare import boundary_mask, rel_err
+    out, gv, gl, ga = got
+    wout, wgv, wgl, wga = want
+    n = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    keep = ~boundary_mask(n(x["loc"]), n(x["shapes"]), eps)
+    errs = dict(out=rel_err(out, wout), grad_value=rel_err(gv, wgv), grad_attn=rel_err(ga, wga),
+                grad_loc=rel_err(gl[keep], wgl[keep]) if keep.any() else 0.0, masked=float(1 - keep.mean()))
+    assert errs["out"] <= fwd_tol, errs
+    assert errs["grad_value"] <= bwd_tol and errs["grad_attn"] <= bwd_tol and errs["grad_loc"] <= bwd_tol, errs
+    assert errs["masked"] < 0.01, errs
+    return errs
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors (from the reference's ms_deform_attn_core_pytorch, fp64)
+# ------------------------------------------------------------------------------------------------
+def test_golden_fp64(golden, dev):
+    got = ours(golden, dev, torch.float64)
+    want = tuple(golden[k] for k in ("out", "grad_value", "grad_loc", "grad_attn"))
+    check(got, want, golden, fwd_tol=1e-12, bwd_tol=1e-11, eps=1e-9)
+
+
+def test_golden_fp32(golden, dev):
+    import ocpg_b200
+    got = ours(golden, dev, torch.float32)
+    want = tuple(golden[k] for k in ("out", "grad_value", "grad_loc", "grad_attn"))
+    check(got, want, golden)
+    if golden["name"] == "d32_l4p4":      # production head layout -> must be the sm_100a tiled kernel
+        assert ocpg_b200.lib().msda_kernel_plan(4, 8, 32, 4, 4) == 1
+
+
+def test_golden_fp32_generic_kernel(golden, dev):
+    import ocpg_b200
+    ocpg_b200.set_option("force_generic", 1)
+    try:
+        got = ours(golden, dev, torch.float32)
+    finally:
+        ocpg_b200.set_option("force_generic", 0)
+    check(got, tuple(golden[k] for k in ("out", "grad_value", "grad_loc", "grad_attn")), golden)
+
+
+# ------------------------------------------------------------------------------------------------
+# re-hosted reference tests (models/ops/test.py)
+# ------------------------------------------------------------------------------------------------
+def _ref_test_inputs(dev, D=2):
+    """models/ops/test.py:21-37 input recipe."""
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = torch.rand(N, S, M, D, device=dev) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2, device=dev)
+    attn = torch.rand(N, Lq, M, L, P, device=dev) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return value, shapes, start, loc, attn
+
+
+def test_reference_check_forward_equal_with_pytorch_double(dev):          # test.py:31-44
+    from ocpg_b200 import MSDeformAttnFunction
+    from oracle import msda_grid_sample
+    torch.manual_seed(3)
+    value, shapes, start, loc, attn = _ref_test_inputs(dev)
+    want = msda_grid_sample(value.double(), shapes, loc.double(), attn.double()).cpu()
+    got = MSDeformAttnFunction.apply(value.double(), shapes, start, loc.double(), attn.double(), 2).cpu()
+    assert torch.allclose(got, want)
+
+
+def test_reference_check_forward_equal_with_pytorch_float(dev):           # test.py:47-60
+    from ocpg_b200 import MSDeformAttnFunction
+    from oracle import msda_grid_sample
+    torch.manual_seed(3)
+    value, shapes, start, loc, attn = _ref_test_inputs(dev)
+    want = msda_grid_sample(value, shapes, loc, attn).cpu()
+    got = MSDeformAttnFunction.apply(value, shapes, start, loc, attn, 2).cpu()
+    assert torch.allclose(got, want, rtol=1e-2, atol=1e-3)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-9)                 # and at the north_star tolerance
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])  # test.py:85-86
+def test_reference_check_gradient_numerical(dev, channels):
+    from ocpg_b200 import MSDeformAttnFunction
+    torch.manual_seed(3)
+    value, shapes, start, loc, attn = _ref_test_inputs(dev, channels)
+    value, loc, attn = (t.double().requires_grad_(True) for t in (value, loc, attn))
+    # The reference runs the full (slow) gradcheck for every D; for D > 71 that is ~10^5 kernel launches
+    # each, so the three large-D cases (which only exist to reach other bwd kernel variants in the
+    # reference) use gradcheck's fast mode -- same tolerances, random projections of the Jacobian.
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, start, loc, attn, 2),
+                                    fast_mode=channels > 71)
+
+
+# ------------------------------------------------------------------------------------------------
+# seeded inputs vs the fp64 CPU oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("regime", ["init", "uniform"])
+@pytest.mark.parametrize("hw", [(96, 160), (360, 640)])
+def test_encoder_shapes_vs_oracle(dev, regime, hw):
+    """Lq == S: the tiled query walk.  (360, 640) with 5 frames is BASELINE.json configs[1] itself."""
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 5 if hw[0] == 360 else 3, *hw)
+    x = make_inputs(wl, regime, seed=7)
+    errs = check(ours(x, dev), oracle64(x), x)
+    print(hw, regime, errs)
+
+
+def test_decoder_shape_vs_oracle(dev):
+    """configs[3]: 5 object queries per frame over the full multi-level memory (Lq != S: linear walk)."""
+    from ocpg_b200.workloads import A2D_DECODER, make_inputs
+    for regime in ("init", "uniform"):
+        x = make_inputs(A2D_DECODER, regime, seed=11)
+        check(ours(x, dev), oracle64(x), x)
+
+
+def test_batch_larger_than_im2col_step(dev):
+    """N = 70 > 64 and not a multiple of it: the reference asserts (cu:50-52), the drop-in takes it."""
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 70, 64, 96)
+    x = make_inputs(wl, "uniform", seed=5)
+    check(ours(x, dev), oracle64(x), x)
+
+
+def test_gapped_level_start_index_falls_back_to_linear_walk(dev):
+    """Lq == S but the levels do not tile [0, S) densely (gaps before each level): still correct."""
+    g = torch.Generator().manual_seed(2)
+    shapes = torch.tensor([(5, 7), (3, 4)])
+    start = torch.tensor([3, 45])
+    S = 45 + 12 + 2
+    N, M, D, L, P, Lq = 2, 8, 32, 2, 4, S
+    x = dict(value=torch.randn(N, S, M, D, generator=g), shapes=shapes, start=start,
+             loc=torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.2 - 0.1,
+             attn=torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P),
+             grad_out=torch.randn(N, Lq, M * D, generator=g))
+    check(ours(x, dev), oracle64(x), x)
+
+
+@pytest.mark.parametrize("L,P", [(1, 1), (2, 3), (3, 8), (4, 8), (5, 4), (16, 2), (4, 9)])
+def test_level_point_combinations(dev, L, P):
+    """D = 32 with other L / P: 1..4 staging rounds of the tiled kernel, and (4, 9) -> generic."""
+    g = torch.Generator().manual_seed(L * 100 + P)
+    hw = [(max(1, 12 >> l), max(1, 10 >> l)) for l in range(L)]
+    shapes = torch.tensor(hw)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, M, D, Lq = 2, 3, 32, S
+    x = dict(value=torch.randn(N, S, M, D, generator=g), shapes=shapes, start=start,
+             loc=torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.3 - 0.15,
+             attn=torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P),
+             grad_out=torch.randn(N, Lq, M * D, generator=g))
+    check(ours(x, dev), oracle64(x), x)
+
+
+def test_empty_query_and_batch(dev):
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    shapes = torch.tensor([[2, 3]], device=dev); start = torch.tensor([0], device=dev)
+    v = torch.ones(1, 6, 2, 32, device=dev)
+    loc = torch.zeros(1, 0, 2, 1, 2, 2, device=dev); attn = torch.zeros(1, 0, 2, 1, 2, device=dev)
+    out = MSDA.ms_deform_attn_forward(v, shapes, start, loc, attn, 64)
+    assert out.shape == (1, 0, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, shapes, start, loc, attn, torch.zeros(1, 0, 64, device=dev), 64)
+    assert gv.shape == v.shape and not gv.any() and gl.numel() == 0 and ga.numel() == 0
+
+
+def test_nonfinite_locations_are_out_of_range(dev):
+    """NaN / inf locations fail the reference's range test (cuh:288): zero contribution, zero grads."""
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 1, 64, 64)
+    x = make_inputs(wl, "init", seed=1)
+    x["loc"][0, ::7, :, 1, 2, 0] = float("nan")
+    x["loc"][0, ::5, :, 2, 1, 1] = float("inf")
+    out, gv, gl, ga = ours(x, dev)
+    assert np.isfinite(out).all() and np.isfinite(gv).all() and np.isfinite(gl).all() and np.isfinite(ga).all()
+    assert not gl[0, ::7, :, 1, 2].any() and not ga[0, ::5, :, 2, 1].any()
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 value
+# ------------------------------------------------------------------------------------------------
+def test_bf16_value_vs_oracle(dev):
+    """Tolerance: against the fp64 oracle fed the bf16-ROUNDED value and grad_output (isolates kernel
+    arithmetic from input quantisation): fp32-emitted grads 1e-4; bf16-emitted out / grad_value
+    2^-8 = 3.9e-3 (one bf16 rounding of the result)."""
+    from oracle.compare import boundary_mask, rel_err
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 3, 96, 160)
+    for regime in ("init", "uniform"):
+        x = make_inputs(wl, regime, seed=9)
+        x["value"] = x["value"].bfloat16().float()
+        x["grad_out"] = x["grad_out"].bfloat16().float()
+        out, gv, gl, ga = ours(x, dev, torch.float32, value_dtype=torch.bfloat16)
+        wout, wgv, wgl, wga = oracle64(x)
+        keep = ~boundary_mask(x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
+        assert rel_err(out, wout) <= 2 ** -8 and rel_err(gv, wgv) <= 2 ** -8
+        assert rel_err(ga, wga) <= BWD_TOL and rel_err(gl[keep], wgl[keep]) <= BWD_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own CUDA op, rebuilt for sm_100a (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def test_against_reference_cuda_op(dev):
+    from oracle import build_ref_cuda
+    from oracle.compare import boundary_mask, rel_err
+    if not os.path.exists(build_ref_cuda.SO):
+        pytest.skip("oracle/_ref/MultiScaleDeformableAttention_ref.so not built")
+    ref = build_ref_cuda.load()
+    from ocpg_b200.workloads import A2D_ENCODER, make_inputs
+    for regime in ("init", "uniform"):
+        x = make_inputs(A2D_ENCODER, regime, seed=21, device=dev)
+        rout = ref.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
+        rgv, rgl, rga = ref.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"],
+                                                    x["grad_out"], 64)
+        out, gv, gl, ga = ours(x, dev)
+        keep = ~boundary_mask(x["loc"], x["shapes"], 1e-4)
+        f = lambda t: t.double().cpu().numpy()
+        assert rel_err(out, f(rout)) <= FWD_TOL
+        assert rel_err(gv, f(rgv)) <= BWD_TOL and rel_err(ga, f(rga)) <= BWD_TOL
+        assert rel_err(gl[keep], f(rgl)[keep]) <= BWD_TOL
+        # same coordinate rounding as the reference kernel: identical cells everywhere, no mask needed
+        assert rel_err(gl, f(rgl)) <= BWD_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[2]: YTVOS shape, N=10, S=Lq=15300)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("regime", ["init", "uniform"])
+def test_full_size_adjoint_linearity_determinism(dev, regime):
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    from ocpg_b200.workloads import YTVOS_ENCODER, make_inputs
+    x = make_inputs(YTVOS_ENCODER, regime, seed=3, device=dev)
+    f = lambda v, a: MSDA.ms_deform_attn_forward(v, x["shapes"], x["start"], x["loc"], a, 64)
+    out = f(x["value"], x["attn"])
+    gv, gl, ga = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["grad_out"], 64)
+    # adjoint identities: the op is linear in value and in attn, so <g, f(v,a)> = <grad_value, v> = <grad_attn, a>
+    lhs = (x["grad_out"].double() * out.double()).sum().item()
+    rhs_v = (gv.double() * x["value"].double()).sum().item()
+    rhs_a = (ga.double() * x["attn"].double()).sum().item()
+    scale = (x["grad_out"].double().abs() * out.double().abs()).sum().item()
+    assert abs(lhs - rhs_v) <= 1e-6 * scale and abs(lhs - rhs_a) <= 1e-6 * scale, (lhs, rhs_v, rhs_a, scale)
+    # linearity in value
+    v2 = torch.randn_like(x["value"])
+    mix = f(2.5 * x["value"] + v2, x["attn"])
+    ref = 2.5 * out + f(v2, x["attn"])
+    assert (mix - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    # constant field: every fully-interior sample returns the constant; weights sum to 1 -> out <= 1
+    ones = f(torch.ones_like(x["value"]), x["attn"])
+    assert ones.max().item() <= 1 + 1e-5 and ones.min().item() >= -1e-6
+    if regime == "init":
+        assert (ones > 1 - 1e-5).float().mean().item() > 0.5
+    # determinism: everything except the atomically accumulated grad_value is bitwise reproducible
+    out2 = f(x["value"], x["attn"])
+    gv2, gl2, ga2 = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["grad_out"], 64)
+    assert torch.equal(out, out2) and torch.equal(gl, gl2) and torch.equal(ga, ga2)
+    assert (gv - gv2).abs().max().item() <= 1e-5 * gv.abs().max().item()
+    # out-of-range points get exactly zero gradient (cuh:365-374 leaves the zero initialisation)
+    W = x["shapes"][:, 1].view(1, 1, 1, -1, 1).float(); H = x["shapes"][:, 0].view(1, 1, 1, -1, 1).float()
+    px, py = x["loc"][..., 0] * W - 0.5, x["loc"][..., 1] * H - 0.5
+    oob = ~((py > -1) & (px > -1) & (py < H) & (px < W))
+    assert not ga[oob].any() and not gl[oob].any()
+
+
+# ------------------------------------------------------------------------------------------------
+# the module and the autograd operator
+# ------------------------------------------------------------------------------------------------
+class _OracleModule(torch.nn.Module):
+    """The reference module's math (ms_deform_attn.py:92-118) with the op replaced by the grid_sample port."""
+
+    def __init__(self, m):
+        super().__init__()
+        self.m = m
+
+    def forward(self, query, reference_points, input_flatten, shapes, start, mask=None):
+        import torch.nn.functional as F
+        from oracle import msda_grid_sample
+        m = self.m
+        N, Lq, _ = query.shape
+        S = input_flatten.shape[1]
+        value = m.value_proj(input_flatten)
+        if mask is not None:
+            value = value.masked_fill(mask[..., None], 0.0)
+        value = value.view(N, S, m.n_heads, m.d_model // m.n_heads)
+        off = m.sampling_offsets(query).view(N, Lq, m.n_heads, m.n_levels, m.n_points, 2)
+        aw = F.softmax(m.attention_weights(query).view(N, Lq, m.n_heads, -1), -1).view(N, Lq, m.n_heads, m.n_levels, m.n_points)
+        if reference_points.shape[-1] == 2:
+            norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+            loc = reference_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+        else:
+            loc = reference_points[:, :, None, :, None, :2] + off / m.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
+        return m.output_proj(msda_grid_sample(value, shapes, loc, aw)), loc, aw
+
+
+@pytest.mark.parametrize("ref_dim,use_mask", [(2, False), (2, True), (4, False)])
+def test_module_end_to_end(dev, ref_dim, use_mask):
+    from ocpg_b200 import MSDeformAttn
+    from oracle.compare import rel_err
+    torch.manual_seed(0)
+    mod = MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():                                  # make offsets / logits depend on the query
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    ref = _OracleModule(copy.deepcopy(mod).double())
+    shapes = torch.tensor([(12, 20), (6, 10), (3, 5), (2, 3)], device=dev)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, Lq = 2, (S if ref_dim == 2 else 5)
+    src = torch.randn(N, S, 256, device=dev)
+    query = torch.randn(N, Lq, 256, device=dev)
+    refp = torch.rand(N, Lq, 4, ref_dim, device=dev)
+    if ref_dim == 4:
+        refp[..., 2:] = refp[..., 2:] * 0.3 + 0.05
+    mask = (torch.rand(N, S, device=dev) < 0.1) if use_mask else None
+    src.requires_grad_(True); query.requires_grad_(True)
+    out, loc, aw = mod(query, refp, src, shapes, start, mask)
+    assert loc.shape == (N, Lq, 8, 4, 4, 2) and aw.shape == (N, Lq, 8, 4, 4)      # 3-tuple, reference :118
+    g = torch.randn_like(out)
+    out.backward(g)
+    src64, q64 = src.detach().double().requires_grad_(True), query.detach().double().requires_grad_(True)
+    rout, rloc, raw = ref(q64, refp.double(), src64, shapes, start, mask)
+    rout.backward(g.double())
+    assert rel_err(out, rout) <= 5e-5 and rel_err(loc, rloc) <= 1e-6 and rel_err(aw, raw) <= 1e-6
+    assert rel_err(src.grad, src64.grad) <= 2e-4 and rel_err(query.grad, q64.grad) <= 2e-3
+    for (n1, p1), (n2, p2) in zip(mod.named_parameters(), ref.m.named_parameters()):
+        assert n1 == n2 and rel_err(p1.grad, p2.grad) <= 2e-3, n1
+
+
+def test_autograd_function_grads_and_none_slots(dev):
+    from ocpg_b200 import MSDeformAttnFunction
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 2, 64, 96)
+    x = make_inputs(wl, "init", seed=4, device=dev)
+    v, s, a = (x[k].clone().requires_grad_(True) for k in ("value", "loc", "attn"))
+    out = MSDeformAttnFunction.apply(v, x["shapes"], x["start"], s, a, 64)
+    out.backward(x["grad_out"][:, :, :].transpose(0, 1).contiguous().transpose(0, 1))   # non-contiguous grad
+    assert v.grad is not None and s.grad is not None and a.grad is not None
+    assert x["shapes"].grad is None and x["start"].grad is None
+    want = oracle64(x)
+    check((out.detach().double().cpu().numpy(), v.grad.double().cpu().numpy(), s.grad.double().cpu().numpy(),
+           a.grad.double().cpu().numpy()), want, x)
+
+
+def test_stream_ordering_and_cuda_graph(dev):
+    """The C ABI enqueues on the caller's current stream without synchronising or allocating, so it can
+    be captured into a CUDA graph and replayed."""
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 2, 96, 160)
+    x = make_inputs(wl, "init", seed=8, device=dev)
+    args = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"])
+    eager_out = MSDA.ms_deform_attn_forward(*args, 64)
+    eager_g = MSDA.ms_deform_attn_backward(*args, x["grad_out"], 64)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        side_out = MSDA.ms_deform_attn_forward(*args, 64)
+    s.synchronize()
+    assert torch.equal(side_out, eager_out)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cap_out = MSDA.ms_deform_attn_forward(*args, 64)
+        cap_g = MSDA.ms_deform_attn_backward(*args, x["grad_out"], 64)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cap_out, eager_out) and torch.equal(cap_g[1], eager_g[1]) and torch.equal(cap_g[2], eager_g[2])
+    assert (cap_g[0] - eager_g[0]).abs().max().item() <= 1e-5 * eager_g[0].abs().max().item()
+
+
+def test_bench_line_contract(dev):
+    """bench.py prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "6", "--warmup", "3", "--input-sets", "2",
+                        "--cpu-seconds", "4"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in line, k
+    assert line["gpu_launches"] == 12 and line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["roofline"]["bound"] == "hbm" and 0 < line["roofline"]["frac"] < 1.5
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
