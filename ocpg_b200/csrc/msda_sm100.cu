@@ -98,77 +98,57 @@ __device__ __forceinline__ float ld_stream_f1(const float *p) {
     asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-__device__ __forceinline__ float4 ld_stream_f4(const float *p) {
-    float4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void red_add_f4(float *p, float a, float b, float c, float d) {
+// grad_value[p .. p+3] += s * {lo.x, lo.y, hi.x, hi.y}: one REDG.E.ADD.F32x4 (sm_90+), no return value.
+__device__ __forceinline__ void red_add_row(const char *p, float s, float2 lo, float2 hi) {
+    const float2 a = __fmul2_rn(make_float2(s, s), lo), b = __fmul2_rn(make_float2(s, s), hi);
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
+__device__ __forceinline__ const char *at(const char *base, int off) { return base + (uint32_t)off; }
 
-// Four channels of one row, as fp32, from fp32 or bf16 storage.  `unit` indexes groups of 4 channels.
-template <typename VT> struct Row4;
-template <> struct Row4<float> {
-    static __device__ __forceinline__ float4 load(const float *base, int64_t unit) {
-        return __ldg(reinterpret_cast<const float4 *>(base) + unit);
-    }
-    static __device__ __forceinline__ void store(float *base, int64_t unit, float4 v) {
-        reinterpret_cast<float4 *>(base)[unit] = v;
-    }
-};
-template <> struct Row4<__nv_bfloat16> {
-    static __device__ __forceinline__ float4 load(const __nv_bfloat16 *base, int64_t unit) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(base) + unit);
-        float4 v;
-        v.x = __uint_as_float(raw.x << 16);
-        v.y = __uint_as_float(raw.x & 0xffff0000u);
-        v.z = __uint_as_float(raw.y << 16);
-        v.w = __uint_as_float(raw.y & 0xffff0000u);
-        return v;
-    }
-    static __device__ __forceinline__ void store(__nv_bfloat16 *base, int64_t unit, float4 v) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-        uint2 raw;
-        raw.x = *reinterpret_cast<uint32_t *>(&lo);
-        raw.y = *reinterpret_cast<uint32_t *>(&hi);
-        reinterpret_cast<uint2 *>(base)[unit] = raw;
-    }
-};
-
-// One sample point, as staged in shared memory for the lanes that gather.
-//   o0 / o1: offset (in units of 4 channels, relative to the frame+head base) of the (y0, x0) and
-//            (y0+1, x0) corners; the x0+1 corners are one pixel (= M*8 units) further.  Row offsets
-//            are multiples of 8, so bit 0 / bit 1 carry the validity of the x0 / x0+1 corner of that row.
-//   lx, ly : fractional position inside the cell (0 when the point is out of range).
+// One sample point as the lanes that gather need it.
+//   o[4]    : byte offsets (inside the frame+head slice of `value`) of the corners (y0,x0), (y0,x0+1),
+//             (y0+1,x0), (y0+1,x0+1).  Rows / columns that fall outside the level are CLAMPED
+//             onto the nearest valid one and their bilinear weight is zeroed instead: every load is in
+//             bounds and unpredicated, and zero padding comes out of the weights (cuh:56-78).
+//   w[4]    : bilinear weights hy*hx, hy*lx, ly*hx, ly*lx, zero for invalid corners / out-of-range points.
 struct PointGeo {
-    int o0, o1;
+    int o00, o01, o10, o11;
+    float w00, w01, w10, w11;
     float lx, ly;
-    bool in_range;
+    int valid;      // bit i: corner i contributes (00, 01, 10, 11)
 };
 
-// Pixel coordinates exactly as the reference forms them: fl(fl(loc * size) - 0.5)
-// (ms_deform_im2col_cuda.cuh:285-286; the 0.5 is a double literal there, which rounds the same way
-// but forbids contraction into an FMA), range test of :288, corner tests of :56/:62/:68/:74.
-__device__ __forceinline__ PointGeo point_geometry(float loc_x, float loc_y, int H, int W, int level_base_units,
-                                                   int units_per_pixel) {
+// Pixel coordinates exactly as the reference's compiled kernel forms them: fma(loc, size, -0.5)
+// (ms_deform_im2col_cuda.cuh:285-286; nvcc contracts the expression -- SASS of the reference op built for
+// sm_100a: `FFMA R29, R12, R29, -0.5` -- so borderline points fall into the same bilinear cell as there),
+// range test of :288, corner tests of :56/:62/:68/:74.
+__device__ __forceinline__ PointGeo point_geometry(float loc_x, float loc_y, int H, int W, int level_base_bytes,
+                                                   int pixel_bytes) {
     PointGeo g;
     const float fw = (float)W, fh = (float)H;
-    const float x = __fadd_rn(__fmul_rn(loc_x, fw), -0.5f);
-    const float y = __fadd_rn(__fmul_rn(loc_y, fh), -0.5f);
-    g.in_range = (y > -1.f) && (x > -1.f) && (y < fh) && (x < fw);
+    const float x = fmaf(loc_x, fw, -0.5f);
+    const float y = fmaf(loc_y, fh, -0.5f);
+    const bool in_range = (y > -1.f) && (x > -1.f) && (y < fh) && (x < fw);   // false for NaN / inf
     const float xf = floorf(x), yf = floorf(y);
-    // out-of-range (or non-finite) points get a harmless cell so that no NaN reaches the sums
-    const int x0 = g.in_range ? (int)xf : 0, y0 = g.in_range ? (int)yf : 0;
-    g.lx = g.in_range ? x - xf : 0.f;
-    g.ly = g.in_range ? y - yf : 0.f;
-    const bool xa = g.in_range && x0 >= 0, xb = g.in_range && x0 + 1 <= W - 1;
-    const bool ya = y0 >= 0, yb = y0 + 1 <= H - 1;
-    const int row0 = level_base_units + (y0 * W + x0) * units_per_pixel;
-    g.o0 = row0 | (int)(xa && ya) | ((int)(xb && ya) << 1);
-    g.o1 = (row0 + W * units_per_pixel) | (int)(xa && yb) | ((int)(xb && yb) << 1);
+    const int x0 = (int)xf, y0 = (int)yf;     // saturating conversion; clamped below when out of range
+    g.lx = in_range ? x - xf : 0.f;
+    g.ly = in_range ? y - yf : 0.f;
+    const float hx = 1.f - g.lx, hy = 1.f - g.ly;
+    const bool xa = in_range && x0 >= 0, xb = in_range && x0 + 1 <= W - 1;
+    const bool ya = in_range && y0 >= 0, yb = in_range && y0 + 1 <= H - 1;
+    const int xs = min(max(x0, -1), W - 1), ys = min(max(y0, -1), H - 1);   // [-1, size-1]: no overflow below
+    const int xc0 = max(xs, 0), xc1 = min(xs + 1, W - 1), yc0 = max(ys, 0), yc1 = min(ys + 1, H - 1);
+    const int dx = (xc1 - xc0) * pixel_bytes;
+    g.o00 = level_base_bytes + (yc0 * W + xc0) * pixel_bytes;
+    g.o10 = level_base_bytes + (yc1 * W + xc0) * pixel_bytes;
+    g.o01 = g.o00 + dx;
+    g.o11 = g.o10 + dx;
+    g.w00 = (xa && ya) ? hy * hx : 0.f;
+    g.w01 = (xb && ya) ? hy * g.lx : 0.f;
+    g.w10 = (xa && yb) ? g.ly * hx : 0.f;
+    g.w11 = (xb && yb) ? g.ly * g.lx : 0.f;
+    g.valid = (int)(xa && ya) | ((int)(xb && ya) << 1) | ((int)(xa && yb) << 2) | ((int)(xb && yb) << 3);
     return g;
 }
 
@@ -219,9 +199,44 @@ __device__ __forceinline__ void load_level_table(LevelTable &lt, const int64_t *
     __syncthreads();
 }
 
+// Packed fp32 pairs: Blackwell's FFMA2 / FMUL2 do two lanes of fp32 math per issue slot, with a scalar
+// operand broadcast for free -- the kernels are issue-bound, so every row update is written in pairs.
+__device__ __forceinline__ float2 fma2s(float s, float2 v, float2 acc) { return __ffma2_rn(make_float2(s, s), v, acc); }
+__device__ __forceinline__ float2 mul2s(float s, float2 v) { return __fmul2_rn(make_float2(s, s), v); }
+struct Row {            // four channels as two pairs
+    float2 lo, hi;
+};
+template <typename VT> struct RowIO;
+template <> struct RowIO<float> {
+    static constexpr int kBytes = 16;          // bytes of four channels
+    static __device__ __forceinline__ Row load(const char *p) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        return Row{make_float2(v.x, v.y), make_float2(v.z, v.w)};
+    }
+    static __device__ __forceinline__ void store(char *p, Row r) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r.lo.x, r.lo.y, r.hi.x, r.hi.y);
+    }
+};
+template <> struct RowIO<__nv_bfloat16> {
+    static constexpr int kBytes = 8;
+    static __device__ __forceinline__ Row load(const char *p) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p));
+        return Row{make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u)),
+                   make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u))};
+    }
+    static __device__ __forceinline__ void store(char *p, Row r) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(r.lo.x, r.lo.y), hi = __floats2bfloat162_rn(r.hi.x, r.hi.y);
+        uint2 raw;
+        raw.x = *reinterpret_cast<uint32_t *>(&lo);
+        raw.y = *reinterpret_cast<uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(p) = raw;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Tiled forward, D = 32.  grid: persistent, CTA b takes tasks b, b+grid, ... ; a task is
-// (frame n, query tile, head m), m fastest.  ROUNDS = ceil(L*P / 8).
+// (frame n, query tile, head m), m fastest.  ROUNDS = ceil(L*P / 8); a round stages 8 points per lane
+// group (slots past L*P carry zero weights), then gathers them branch-free.
 // ------------------------------------------------------------------------------------------------
 template <typename VT, int ROUNDS>
 __global__ void __launch_bounds__(kWarps * 32, 2)
@@ -229,14 +244,14 @@ msda_fwd_tiled(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const float *__restrict__ loc, const float *__restrict__ attn, VT *__restrict__ out, Dims d) {
     __shared__ LevelTable lt;
     __shared__ float4 s_w[kWarps][4][kPad];   // a*w00, a*w01, a*w10, a*w11
-    __shared__ int2 s_o[kWarps][4][kPad];     // o0, o1
+    __shared__ int4 s_o[kWarps][4][kPad];     // byte offsets of the four corners
     load_level_table(lt, shapes, start, d.L, d.Lq);
     const bool tiled = d.tiled && lt.dense;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, cl = lane & 7;
     const int pts = d.L * d.P;
-    const int upp = d.M * 8;                  // units (4 channels) per pixel
+    const int pixel_bytes = d.M * 32 * (int)sizeof(VT);
     int lvl[ROUNDS];
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) lvl[r] = min((8 * r + cl) / d.P, d.L - 1);
@@ -250,55 +265,56 @@ msda_fwd_tiled(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         const QuerySel qs = select_query(tiled, d, lt, tile, warp, grp);
         if (!__any_sync(0xffffffffu, qs.valid)) continue;
         const int64_t row = (n * d.Lq + qs.q) * d.M + m;              // (n, q, m)
-        const int64_t frame_unit = (n * d.S * d.M + m) * 8;           // frame n, head m, in units
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // frame n, head m, this lane's four channels
+        const char *vb = reinterpret_cast<const char *>(value) +
+                         ((n * d.S * d.M + m) * 32 + cl * 4) * (int64_t)sizeof(VT);
+        float2 acc_lo = make_float2(0.f, 0.f), acc_hi = make_float2(0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int pt = 8 * r + cl;
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            int2 o = make_int2(0, 0);
+            int4 o = make_int4(0, 0, 0, 0);
             if (qs.valid && pt < pts) {
                 const float2 xy = ld_stream_f2(loc + (row * pts + pt) * 2);
                 const float a = ld_stream_f1(attn + row * pts + pt);
                 const int l = lvl[r];
-                const PointGeo g = point_geometry(xy.x, xy.y, lt.H[l], lt.W[l], lt.start[l] * upp, upp);
-                const float hx = 1.f - g.lx, hy = 1.f - g.ly;
-                const float aa = g.in_range ? a : 0.f;
-                w = make_float4(aa * (hy * hx), aa * (hy * g.lx), aa * (g.ly * hx), aa * (g.ly * g.lx));
-                o = make_int2(g.o0, g.o1);
+                const PointGeo g = point_geometry(xy.x, xy.y, lt.H[l], lt.W[l], lt.start[l] * pixel_bytes, pixel_bytes);
+                w = make_float4(a * g.w00, a * g.w01, a * g.w10, a * g.w11);
+                o = make_int4(g.o00, g.o01, g.o10, g.o11);
             }
             s_w[warp][grp][cl] = w;
             s_o[warp][grp][cl] = o;
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                if (8 * r + it < pts) {
-                    const float4 pw = s_w[warp][grp][it];
-                    const int2 po = s_o[warp][grp][it];
-                    const int64_t u0 = frame_unit + ((po.x & ~7) | cl), u1 = frame_unit + ((po.y & ~7) | cl);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 v00 = (po.x & 1) ? Row4<VT>::load(value, u0) : z;
-                    const float4 v01 = (po.x & 2) ? Row4<VT>::load(value, u0 + upp) : z;
-                    const float4 v10 = (po.y & 1) ? Row4<VT>::load(value, u1) : z;
-                    const float4 v11 = (po.y & 2) ? Row4<VT>::load(value, u1 + upp) : z;
-                    acc.x = fmaf(pw.x, v00.x, acc.x); acc.y = fmaf(pw.x, v00.y, acc.y);
-                    acc.z = fmaf(pw.x, v00.z, acc.z); acc.w = fmaf(pw.x, v00.w, acc.w);
-                    acc.x = fmaf(pw.y, v01.x, acc.x); acc.y = fmaf(pw.y, v01.y, acc.y);
-                    acc.z = fmaf(pw.y, v01.z, acc.z); acc.w = fmaf(pw.y, v01.w, acc.w);
-                    acc.x = fmaf(pw.z, v10.x, acc.x); acc.y = fmaf(pw.z, v10.y, acc.y);
-                    acc.z = fmaf(pw.z, v10.z, acc.z); acc.w = fmaf(pw.z, v10.w, acc.w);
-                    acc.x = fmaf(pw.w, v11.x, acc.x); acc.y = fmaf(pw.w, v11.y, acc.y);
-                    acc.z = fmaf(pw.w, v11.z, acc.z); acc.w = fmaf(pw.w, v11.w, acc.w);
-                }
+                const float4 pw = s_w[warp][grp][it];
+                const int4 po = s_o[warp][grp][it];
+                const Row v00 = RowIO<VT>::load(at(vb, po.x));
+                const Row v01 = RowIO<VT>::load(at(vb, po.y));
+                const Row v10 = RowIO<VT>::load(at(vb, po.z));
+                const Row v11 = RowIO<VT>::load(at(vb, po.w));
+                acc_lo = fma2s(pw.x, v00.lo, acc_lo); acc_hi = fma2s(pw.x, v00.hi, acc_hi);
+                acc_lo = fma2s(pw.y, v01.lo, acc_lo); acc_hi = fma2s(pw.y, v01.hi, acc_hi);
+                acc_lo = fma2s(pw.z, v10.lo, acc_lo); acc_hi = fma2s(pw.z, v10.hi, acc_hi);
+                acc_lo = fma2s(pw.w, v11.lo, acc_lo); acc_hi = fma2s(pw.w, v11.hi, acc_hi);
             }
             __syncwarp();
         }
-        if (qs.valid) Row4<VT>::store(out, row * 8 + cl, acc);
+        if (qs.valid)
+            RowIO<VT>::store(reinterpret_cast<char *>(out) + (row * 32 + cl * 4) * (int64_t)sizeof(VT), Row{acc_lo, acc_hi});
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Tiled backward, D = 32.  Same task walk as the forward.  grad_value (fp32) must be zero on entry.
+//
+// Per point and per lane (4 channels) the loop only forms the four corner dot products
+//     p_i = sum_c grad_out[c] * v_i[c]
+// and the scatter rows (a * w_i) * grad_out.  The 8-lane sums of p_i land, transposed, in the lane that
+// owns the point, which finishes with scalars (cuh:123-158 regrouped by corner):
+//     grad_attn = sum_i w_i p_i
+//     grad_x    = W * a * ( hy (p01 - p00) + ly (p11 - p10) )      (invalid corners dropped)
+//     grad_y    = H * a * ( hx (p10 - p00) + lx (p11 - p01) )
 // ------------------------------------------------------------------------------------------------
 // Sum v[0..7] across the 8 lanes of a group so that lane `cl` ends with the total of v[cl]:
 // 7 shuffles instead of 24 for eight separate butterfly reductions.
@@ -319,6 +335,11 @@ __device__ __forceinline__ float transpose_reduce8(const float (&v)[8], int cl) 
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+__device__ __forceinline__ float dot4(const Row &a, const Row &b) {
+    const float2 t = __ffma2_rn(a.hi, b.hi, __fmul2_rn(a.lo, b.lo));
+    return t.x + t.y;
+}
+
 template <typename VT, int ROUNDS>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
@@ -326,14 +347,15 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d) {
     __shared__ LevelTable lt;
     __shared__ float4 s_w[kWarps][4][kPad];   // a*w00, a*w01, a*w10, a*w11   (scatter weights)
-    __shared__ float4 s_g[kWarps][4][kPad];   // lx, ly, o0, o1 (ints as bits)
+    __shared__ int4 s_o[kWarps][4][kPad];     // byte offsets of the four corners
     load_level_table(lt, shapes, start, d.L, d.Lq);
     const bool tiled = d.tiled && lt.dense;
+    constexpr int kGradScale = 4 / (int)sizeof(VT);   // grad_value is fp32: its byte offsets are this x value's
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, cl = lane & 7;
     const int pts = d.L * d.P;
-    const int upp = d.M * 8;
+    const int pixel_bytes = d.M * 32 * (int)sizeof(VT);
     int lvl[ROUNDS];
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) lvl[r] = min((8 * r + cl) / d.P, d.L - 1);
@@ -347,75 +369,74 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
         const QuerySel qs = select_query(tiled, d, lt, tile, warp, grp);
         if (!__any_sync(0xffffffffu, qs.valid)) continue;
         const int64_t row = (n * d.Lq + qs.q) * d.M + m;
-        const int64_t frame_unit = (n * d.S * d.M + m) * 8;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 go = qs.valid ? Row4<VT>::load(grad_out, row * 8 + cl) : z;
+        const int64_t slice = (n * d.S * d.M + m) * 32 + cl * 4;      // element offset of frame n, head m, 4 channels
+        const char *vb = reinterpret_cast<const char *>(value) + slice * (int64_t)sizeof(VT);
+        const char *gb = reinterpret_cast<const char *>(grad_value) + slice * 4;
+        Row go{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if (qs.valid) go = RowIO<VT>::load(reinterpret_cast<const char *>(grad_out) + (row * 32 + cl * 4) * (int64_t)sizeof(VT));
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int pt = 8 * r + cl;
-            float4 w = z, gq = z;
-            float a_own = 0.f, fw_own = 0.f, fh_own = 0.f;   // this lane's point: attn, W_l, H_l
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            int4 o = make_int4(0, 0, 0, 0);
+            PointGeo own;                                   // this lane's own point, kept for the epilogue
+            own.w00 = own.w01 = own.w10 = own.w11 = own.lx = own.ly = 0.f;
+            own.valid = 0;
+            float a_own = 0.f, fw_own = 0.f, fh_own = 0.f;
             if (qs.valid && pt < pts) {
                 const float2 xy = ld_stream_f2(loc + (row * pts + pt) * 2);
-                const float a = ld_stream_f1(attn + row * pts + pt);
+                a_own = ld_stream_f1(attn + row * pts + pt);
                 const int l = lvl[r];
-                const PointGeo g = point_geometry(xy.x, xy.y, lt.H[l], lt.W[l], lt.start[l] * upp, upp);
-                const float hx = 1.f - g.lx, hy = 1.f - g.ly;
-                a_own = g.in_range ? a : 0.f;
+                own = point_geometry(xy.x, xy.y, lt.H[l], lt.W[l], lt.start[l] * pixel_bytes, pixel_bytes);
                 fw_own = (float)lt.W[l];
                 fh_own = (float)lt.H[l];
-                w = make_float4(a_own * (hy * hx), a_own * (hy * g.lx), a_own * (g.ly * hx), a_own * (g.ly * g.lx));
-                gq = make_float4(g.lx, g.ly, __int_as_float(g.o0), __int_as_float(g.o1));
+                w = make_float4(a_own * own.w00, a_own * own.w01, a_own * own.w10, a_own * own.w11);
+                o = make_int4(own.o00, own.o01, own.o10, own.o11);
             }
             s_w[warp][grp][cl] = w;
-            s_g[warp][grp][cl] = gq;
+            s_o[warp][grp][cl] = o;
             __syncwarp();
-            float sa[8], sx[8], sy[8];
+            float p00[8], p01[8], p10[8], p11[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                sa[it] = 0.f; sx[it] = 0.f; sy[it] = 0.f;
-                if (8 * r + it < pts) {
-                    const float4 pw = s_w[warp][grp][it];
-                    const float4 pg = s_g[warp][grp][it];
-                    const float lx = pg.x, ly = pg.y;
-                    const int o0 = __float_as_int(pg.z), o1 = __float_as_int(pg.w);
-                    const int64_t u0 = frame_unit + ((o0 & ~7) | cl), u1 = frame_unit + ((o1 & ~7) | cl);
-                    const float4 v00 = (o0 & 1) ? Row4<VT>::load(value, u0) : z;
-                    const float4 v01 = (o0 & 2) ? Row4<VT>::load(value, u0 + upp) : z;
-                    const float4 v10 = (o1 & 1) ? Row4<VT>::load(value, u1) : z;
-                    const float4 v11 = (o1 & 2) ? Row4<VT>::load(value, u1 + upp) : z;
-                    // scatter: grad_value[corner] += (a * w_corner) * grad_out          (cuh:125,134,143,152)
-                    if (!d.debug_skip_scatter) {
-                    if (o0 & 1) red_add_f4(grad_value + u0 * 4, pw.x * go.x, pw.x * go.y, pw.x * go.z, pw.x * go.w);
-                    if (o0 & 2) red_add_f4(grad_value + (u0 + upp) * 4, pw.y * go.x, pw.y * go.y, pw.y * go.z, pw.y * go.w);
-                    if (o1 & 1) red_add_f4(grad_value + u1 * 4, pw.z * go.x, pw.z * go.y, pw.z * go.z, pw.z * go.w);
-                    if (o1 & 2) red_add_f4(grad_value + (u1 + upp) * 4, pw.w * go.x, pw.w * go.y, pw.w * go.z, pw.w * go.w);
-                    }
-                    // per channel: dB/dx = d0 + ly*dd, dB/dy = e0 + lx*dd, B = v00 + lx*d0 + ly*dB/dy
-                    // with d0 = v01-v00, e0 = v10-v00, dd = v11-v10-v01+v00             (cuh:123-158 regrouped)
-#define MSDA_CH(c)                                                                   \
-    {                                                                                \
-        const float d0 = v01.c - v00.c, d1 = v11.c - v10.c, e0 = v10.c - v00.c;      \
-        const float dd = d1 - d0;                                                    \
-        const float gx = fmaf(ly, dd, d0), gy = fmaf(lx, dd, e0);                    \
-        const float b = fmaf(ly, gy, fmaf(lx, d0, v00.c));                           \
-        sa[it] = fmaf(go.c, b, sa[it]);                                              \
-        sx[it] = fmaf(go.c, gx, sx[it]);                                             \
-        sy[it] = fmaf(go.c, gy, sy[it]);                                             \
-    }
-                    MSDA_CH(x) MSDA_CH(y) MSDA_CH(z) MSDA_CH(w)
-#undef MSDA_CH
+                const float4 pw = s_w[warp][grp][it];
+                const int4 po = s_o[warp][grp][it];
+                const Row v00 = RowIO<VT>::load(at(vb, po.x));
+                const Row v01 = RowIO<VT>::load(at(vb, po.y));
+                const Row v10 = RowIO<VT>::load(at(vb, po.z));
+                const Row v11 = RowIO<VT>::load(at(vb, po.w));
+                p00[it] = dot4(go, v00);
+                p01[it] = dot4(go, v01);
+                p10[it] = dot4(go, v10);
+                p11[it] = dot4(go, v11);
+                // scatter: grad_value[corner] += (a * w_corner) * grad_out              (cuh:125,134,143,152)
+                // A point with no contributing corner (out of range, zero attention) is skipped as a whole;
+                // otherwise its clamped corners receive +0, which is harmless.
+                const uint32_t any_w = (__float_as_uint(pw.x) | __float_as_uint(pw.y) | __float_as_uint(pw.z) |
+                                        __float_as_uint(pw.w)) << 1;
+                if (any_w != 0u && !d.debug_skip_scatter) {
+                    red_add_row(at(gb, po.x * kGradScale), pw.x, go.lo, go.hi);
+                    red_add_row(at(gb, po.y * kGradScale), pw.y, go.lo, go.hi);
+                    red_add_row(at(gb, po.z * kGradScale), pw.z, go.lo, go.hi);
+                    red_add_row(at(gb, po.w * kGradScale), pw.w, go.lo, go.hi);
                 }
             }
             __syncwarp();
-            const float ta = transpose_reduce8(sa, cl);
-            const float tx = transpose_reduce8(sx, cl);
-            const float ty = transpose_reduce8(sy, cl);
+            float q00 = transpose_reduce8(p00, cl), q01 = transpose_reduce8(p01, cl);
+            float q10 = transpose_reduce8(p10, cl), q11 = transpose_reduce8(p11, cl);
             if (qs.valid && pt < pts) {
-                // grad_attn = sum_c g*B (:156); grad_loc = (W * a * sum_c g*dB/dx, H * a * sum_c g*dB/dy) (:157-158)
-                grad_attn[row * pts + pt] = ta;
+                // clamped (invalid) corners carry someone else's row: drop them (zero padding, cuh:56-78)
+                q00 = (own.valid & 1) ? q00 : 0.f;
+                q01 = (own.valid & 2) ? q01 : 0.f;
+                q10 = (own.valid & 4) ? q10 : 0.f;
+                q11 = (own.valid & 8) ? q11 : 0.f;
+                const float hx = 1.f - own.lx, hy = 1.f - own.ly;
+                const float ga = own.w00 * q00 + own.w01 * q01 + own.w10 * q10 + own.w11 * q11;       // :156
+                const float gx = hy * (q01 - q00) + own.ly * (q11 - q10);                             // :157
+                const float gy = hx * (q10 - q00) + own.lx * (q11 - q01);                             // :158
+                grad_attn[row * pts + pt] = ga;
                 *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) =
-                    make_float2(fw_own * a_own * tx, fh_own * a_own * ty);
+                    make_float2(fw_own * a_own * gx, fh_own * a_own * gy);
             }
         }
     }
@@ -564,8 +585,8 @@ bool tiled_ok(int channels, int L, int P) {
 int check_dims(int N, int S, int M, int D, int L, int Lq, int P) {
     if (N < 0 || Lq < 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || P <= 0)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda: dimensions must be positive (batch and num_query may be 0)");
-    if ((int64_t)Lq * M * L * P * 2 >= (int64_t)1 << 40 || (int64_t)S * M * D >= (int64_t)1 << 31)
-        return fail(MSDA_ERR_UNSUPPORTED, "msda: a single frame exceeds 2^31 value elements");
+    if ((int64_t)Lq * M * L * P * 2 >= (int64_t)1 << 40 || (int64_t)S * M * D >= (int64_t)1 << 29)
+        return fail(MSDA_ERR_UNSUPPORTED, "msda: a single frame exceeds 2^29 value elements (2 GiB of fp32)");
     return MSDA_OK;
 }
 

@@ -23,15 +23,17 @@
  *   out / grad_out [N][Lq][M*D]
  *
  * The per-point arithmetic is kept in the reference's evaluation order and in the tensor's own
- * scalar type (so the f32 instantiation is a model of the reference CUDA kernel's rounding, up to
- * FMA contraction), the f64 instantiation is the ground truth used for tolerances.
+ * scalar type (so the f32 instantiation is a model of the reference CUDA kernel's rounding), the f64
+ * instantiation is the ground truth used for tolerances.  The pixel coordinate loc*size - 0.5 is a
+ * fused multiply-add: that is what nvcc makes of cuh:285-286 (SASS of the reference op built for
+ * sm_100a: `FFMA R29, R12, R29, -0.5`), so the cell a borderline point falls into is the reference's.
  * Build: see oracle/Makefile (-ffp-contract=off keeps the f32 instantiation deterministic).
  */
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
 
-#define MSDA_ORACLE_DEFINE(SUFFIX, T, FLOOR)                                                        \
+#define MSDA_ORACLE_DEFINE(SUFFIX, T, FLOOR, FMA)                                                       \
                                                                                                     \
 /* One sample point: the four corner indices (or -1), and the four bilinear weights.             */ \
 /* cuh:38-53 for the cell decomposition, cuh:56/62/68/74 for the per-corner validity tests.      */ \
@@ -66,8 +68,8 @@ void msda_oracle_forward_##SUFFIX(const T *value, const int64_t *shapes, const i
             const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];                           \
             const T *vl = value + ((n * S + start[l]) * M + m) * D;   /* cuh:269,278 */             \
             for (int p = 0; p < P; ++p, pl += 2, ++pa) {                                            \
-                const T y = pl[1] * (T)H - (T)0.5;                    /* cuh:285 */                 \
-                const T x = pl[0] * (T)W - (T)0.5;                    /* cuh:286 */                 \
+                const T y = FMA(pl[1], (T)H, (T)-0.5);                /* cuh:285 */                 \
+                const T x = FMA(pl[0], (T)W, (T)-0.5);                /* cuh:286 */                 \
                 if (!(y > (T)-1 && x > (T)-1 && y < (T)H && x < (T)W)) continue; /* cuh:288 */      \
                 long cr[4]; T w[4], fr[4];                                                          \
                 cell_##SUFFIX(y, x, H, W, cr, w, fr);                                               \
@@ -107,8 +109,8 @@ void msda_oracle_backward_##SUFFIX(const T *value, const int64_t *shapes, const 
                 const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];                       \
                 const long base = ((n * S + start[l]) * M + m) * D;                                 \
                 for (int p = 0; p < P; ++p, pl += 2, ++pa, gl += 2, ++ga) {                         \
-                    const T y = pl[1] * (T)H - (T)0.5;                                              \
-                    const T x = pl[0] * (T)W - (T)0.5;                                              \
+                    const T y = FMA(pl[1], (T)H, (T)-0.5);                                          \
+                    const T x = FMA(pl[0], (T)W, (T)-0.5);                                          \
                     if (!(y > (T)-1 && x > (T)-1 && y < (T)H && x < (T)W)) continue; /* :365 */     \
                     long cr[4]; T w[4], fr[4];                                                      \
                     cell_##SUFFIX(y, x, H, W, cr, w, fr);                                           \
@@ -143,7 +145,7 @@ void msda_oracle_backward_##SUFFIX(const T *value, const int64_t *shapes, const 
     }                                                                                               \
 }
 
-MSDA_ORACLE_DEFINE(f32, float, floorf)
-MSDA_ORACLE_DEFINE(f64, double, floor)
+MSDA_ORACLE_DEFINE(f32, float, floorf, fmaf)
+MSDA_ORACLE_DEFINE(f64, double, floor, fma)
 
 int msda_oracle_abi_version(void) { return 1; }
