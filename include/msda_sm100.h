@@ -111,9 +111,16 @@ int msda_kernel_plan(int elem_bytes, int num_heads, int channels, int num_levels
  * used by bench.py to report `gpu_launches`. */
 uint64_t msda_launch_count(void);
 
-/* Tuning knobs for experiments (not needed for normal use).  Known keys: "fwd_ctas_per_sm",
- * "bwd_ctas_per_sm", "force_generic", "force_linear_walk", "debug_skip_scatter" (the last one makes
- * grad_value wrong on purpose: it exists to measure the cost of the scatter).  Returns 0, or MSDA_ERR_INVALID_ARGUMENT for an unknown key. */
+/* Tuning knobs for experiments (not needed for normal use).  Known keys:
+ *   "fwd_warps", "bwd_warps"             8 or 16 warps per CTA (0 = default)
+ *   "fwd_ctas_per_sm", "bwd_ctas_per_sm" resident CTAs per SM the persistent grid is sized for (0 = default)
+ *   "frame_chunk"                        frames whose passes are interleaved by the task walk (0 = automatic)
+ *   "force_generic"                      use the any-shape kernels even when the tiled ones apply
+ *   "force_linear_walk"                  walk queries linearly instead of as spatial tiles
+ *   "bwd_mode"                           1 = backward without the grad_value scatter, 2 = the scatter alone
+ *   "debug_skip_scatter"                 same as bwd_mode 1
+ * (the last two make results wrong on purpose: they exist to measure what bounds the backward).
+ * Returns 0, or MSDA_ERR_INVALID_ARGUMENT for an unknown key. */
 int msda_set_option(const char *key, int value);
 
 #ifdef __cplusplus

@@ -5,20 +5,24 @@
 // behind the C ABI of include/msda_sm100.h.  See DESIGN.md for the data layout and the roofline
 // of each kernel.
 //
-// Why it looks the way it does.  Per (query, head) the op gathers L*P*4 = 64 rows of 32 channels
-// (128 B each in fp32): 8 KB of gather for 448 B of compulsory traffic.  The gather is served by the
-// SM's L1/shared-memory data path (one 128 B wavefront per row), not by HBM, so the kernels are
-// organised around three things:
-//   1. locality: a CTA works on an 8x8 *spatial tile* of queries of ONE head at a time, so the rows its
-//      16 warps gather overlap and stay resident in L1 (the whole of `value` stays resident in the
-//      126 MB L2);
-//   2. few, wide memory instructions: 8 lanes x 128-bit cover one 32-channel row, the four 8-lane
-//      groups of a warp work on four x-adjacent queries, so one LDG.128 / RED.128 moves four rows;
-//   3. few issue slots: the per-point geometry (pixel coordinates, bilinear weights, corner offsets,
-//      validity) is computed once per point by one lane, staged in shared memory, and read back by the
-//      lanes that gather with one or two broadcast LDS.128 per point.
-// The backward replaces the reference's per-channel scalar atomics and its serial 32-term reductions by
-// red.global.add.v4.f32 (one instruction per four rows) and an 8-lane transposing shuffle reduction.
+// Why it looks the way it does.  Per (query, head) the op gathers L*P*4 = 64 rows of 32 channels (128 B each in
+// fp32) and, backward, scatters 64 rows: 8 KB + 8 KB of SM <-> L1/L2 traffic for 448 B of compulsory HBM traffic.
+// Neither is served by HBM.  Measured on this machine (tools/ubench_gather.cu, profiles/r1_ubench_*.jsonl):
+//   - a four-row LDG.128 costs an SM 4.1 cycles when all rows hit L1 and 8.1 cycles when one misses; rows
+//     straight from L2 stream at ~2 cycles each (64 B/clk/SM);
+//   - fp32 reds are bounded CHIP-wide by the L2 atomic units: 6.4 TB/s however they are issued (v4, v2, scalar;
+//     37 or 148 SMs), and far less when many CTAs hit the same few rows.
+// So:
+//   1. few, wide memory instructions: 8 lanes x 128-bit cover one 32-channel row, the four 8-lane groups of a
+//      warp work on four x-adjacent queries, so one LDG.128 / RED.128 moves four rows;
+//   2. few issue slots: the per-point geometry (pixel coordinates, bilinear weights, clamped corner offsets) is
+//      computed once per point by one lane, staged in shared memory, and read back with two broadcast LDS.128;
+//      every load is unpredicated and in bounds (zero padding comes out of the weights);
+//   3. locality: a CTA pass covers an 8x8 (or 8x4) spatial tile of queries of ONE head, whose rows overlap (L1);
+//   4. the backward's reds are predicated off for zero-weight corners, and the persistent CTAs are spread over
+//      all (frame, head) slices at once so that the coarse levels' few rows do not serialise in L2;
+//   5. the backward's per-point reductions go through shared memory (one STS.128 per point, a rotated 8-way
+//      add by the lane that owns the point) instead of 28 shuffles: fewer registers, 32 resident warps.
 //
 // No tensor cores: the op is a gather / scatter with ~0.2 flop per byte.
 
@@ -41,6 +45,10 @@ thread_local char g_err[256] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_fwd_ctas_per_sm{0};   // 0 = kernel default
 std::atomic<int> g_bwd_ctas_per_sm{0};
+std::atomic<int> g_fwd_warps{0};          // 0 = default; 8 or 16 warps per CTA
+std::atomic<int> g_bwd_warps{0};
+std::atomic<int> g_bwd_mode{0};          // experiments: see Dims::bwd_mode
+std::atomic<int> g_unit{0};               // 0 = automatic; frames interleaved by the task walk
 std::atomic<int> g_force_generic{0};
 std::atomic<int> g_force_linear{0};     // experiments: never use the tiled query walk
 std::atomic<int> g_skip_scatter{0};     // experiments: see Dims::debug_skip_scatter
@@ -70,14 +78,21 @@ int sm_count() {
 // device helpers
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxLevels = 16;   // levels the tiled kernels keep in shared memory
-constexpr int kWarps = 16;       // warps per CTA of the tiled kernels (512 threads)
-constexpr int kTile = 8;         // a CTA pass covers an 8 x 8 tile of queries: 16 warps x 4 lane groups
-constexpr int kPad = 9;          // 8 staged points per lane group + 1 slot of padding (bank spread)
+// A CTA of WARPS warps covers, per pass, a TILE_W x TILE_H patch of queries (4 x-adjacent queries per warp):
+//   WARPS = 8: 8 x 4,   16: 8 x 8.
+template <int WARPS> struct Tile {
+    static constexpr int W = WARPS == 32 ? 16 : 8;
+    static constexpr int H = WARPS * 4 / W;
+    static constexpr int kQueries = WARPS * 4;
+    static constexpr int kWarpsPerRow = W / 4;
+};
 
 struct Dims {
-    int N, S, M, L, Lq, P;       // D is a template parameter / 32 for the tiled kernels
+    int N, S, M, L, Lq, P;       // D is 32 for the tiled kernels
     int tiled;                   // 1: Lq == S, walk queries as spatial tiles of their own level
     int debug_skip_scatter;      // experiments only: backward omits the grad_value reds (wrong grad_value)
+    int fchunk;                  // frames whose passes are interleaved (TaskWalk)
+    int bwd_mode;                // experiments only, see msda_bwd_tiled
 };
 
 struct LevelTable {              // shared memory, filled once per CTA from the int64 device tensors
@@ -90,30 +105,94 @@ struct LevelTable {              // shared memory, filled once per CTA from the 
 
 __device__ __forceinline__ float2 ld_stream_f2(const float *p) {
     float2 r;
-    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ float ld_stream_f1(const float *p) {
     float r;
-    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-// grad_value[p .. p+3] += s * {lo.x, lo.y, hi.x, hi.y}: one REDG.E.ADD.F32x4 (sm_90+), no return value.
-__device__ __forceinline__ void red_add_row(const char *p, float s, float2 lo, float2 hi) {
-    const float2 a = __fmul2_rn(make_float2(s, s), lo), b = __fmul2_rn(make_float2(s, s), hi);
-    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+
+// base + unit * sizeof(T) with a 32-bit unit offset in ONE instruction (IMAD.WIDE.U32); plain pointer
+// arithmetic makes nvcc rebuild the 64-bit index and scale it (4 instructions per gathered row).
+template <typename T> __device__ __forceinline__ T *row_at(T *base, uint32_t unit) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(unit), "n"((int)sizeof(T)), "l"(base));
+    return reinterpret_cast<T *>(r);
 }
-__device__ __forceinline__ const char *at(const char *base, int off) { return base + (uint32_t)off; }
+
+// Packed fp32 pairs: Blackwell's FFMA2 / FMUL2 do two lanes of fp32 math per issue slot.
+struct Row {            // four channels as two pairs
+    float2 lo, hi;
+};
+__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+__device__ __forceinline__ void fma_row(float s, const Row &v, Row &acc) {
+    acc.lo = __ffma2_rn(splat(s), v.lo, acc.lo);
+    acc.hi = __ffma2_rn(splat(s), v.hi, acc.hi);
+}
+__device__ __forceinline__ float dot_row(const Row &a, const Row &b) {
+    const float2 t = __ffma2_rn(a.hi, b.hi, __fmul2_rn(a.lo, b.lo));
+    return t.x + t.y;
+}
+
+// Four channels of one (pixel, head) row as stored: a 16-byte (fp32) or 8-byte (bf16) vector.  All row
+// offsets inside the kernels are counted in these vectors ("units"): the same unit index addresses `value`
+// (in its own dtype) and the fp32 `grad_value`.
+template <typename VT> struct RowIO;
+template <> struct RowIO<float> {
+    using Vec = float4;
+    static __device__ __forceinline__ Row load(const Vec *p) {
+        const float4 v = __ldg(p);
+        return Row{make_float2(v.x, v.y), make_float2(v.z, v.w)};
+    }
+    static __device__ __forceinline__ Row load_stream(const Vec *p) {
+        float4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+        return Row{make_float2(v.x, v.y), make_float2(v.z, v.w)};
+    }
+    static __device__ __forceinline__ void store(Vec *p, const Row &r) { *p = make_float4(r.lo.x, r.lo.y, r.hi.x, r.hi.y); }
+};
+template <> struct RowIO<__nv_bfloat16> {
+    using Vec = uint2;
+    static __device__ __forceinline__ Row unpack(uint2 raw) {
+        return Row{make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u)),
+                   make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u))};
+    }
+    static __device__ __forceinline__ Row load(const Vec *p) { return unpack(__ldg(p)); }
+    static __device__ __forceinline__ Row load_stream(const Vec *p) {
+        uint2 raw;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+        return unpack(raw);
+    }
+    static __device__ __forceinline__ void store(Vec *p, const Row &r) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(r.lo.x, r.lo.y), hi = __floats2bfloat162_rn(r.hi.x, r.hi.y);
+        uint2 raw;
+        raw.x = *reinterpret_cast<uint32_t *>(&lo);
+        raw.y = *reinterpret_cast<uint32_t *>(&hi);
+        *p = raw;
+    }
+};
+
+// grad_value row (4 channels of this lane) += s * g: one REDG.E.ADD.F32x4 (sm_90+), no return value.
+// `on` predicates the instruction: a corner whose weight is exactly zero (outside the level, zero
+// attention, out-of-range point) sends nothing -- the reds are what bounds the backward.
+__device__ __forceinline__ void red_row(float4 *p, float s, const Row &g, bool on) {
+    const float2 a = __fmul2_rn(splat(s), g.lo), b = __fmul2_rn(splat(s), g.hi);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+                 "@q red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "r"((uint32_t)on) : "memory");
+}
 
 // One sample point as the lanes that gather need it.
-//   o[4]    : byte offsets (inside the frame+head slice of `value`) of the corners (y0,x0), (y0,x0+1),
-//             (y0+1,x0), (y0+1,x0+1).  Rows / columns that fall outside the level are CLAMPED
-//             onto the nearest valid one and their bilinear weight is zeroed instead: every load is in
-//             bounds and unpredicated, and zero padding comes out of the weights (cuh:56-78).
-//   w[4]    : bilinear weights hy*hx, hy*lx, ly*hx, ly*lx, zero for invalid corners / out-of-range points.
+//   o[4] : unit offsets (inside the frame+head slice of `value`) of the corners (y0,x0), (y0,x0+1), (y0+1,x0),
+//          (y0+1,x0+1).  Rows / columns that fall outside the level are CLAMPED onto the nearest valid one and
+//          their bilinear weight is zeroed instead: every load is in bounds and unpredicated, and the zero
+//          padding of the reference (cuh:56-78) comes out of the weights.
+//   w[4] : bilinear weights hy*hx, hy*lx, ly*hx, ly*lx; zero for invalid corners and out-of-range points.
 struct PointGeo {
-    int o00, o01, o10, o11;
+    uint32_t o00, o01, o10, o11;
     float w00, w01, w10, w11;
     float lx, ly;
     int valid;      // bit i: corner i contributes (00, 01, 10, 11)
@@ -123,27 +202,27 @@ struct PointGeo {
 // (ms_deform_im2col_cuda.cuh:285-286; nvcc contracts the expression -- SASS of the reference op built for
 // sm_100a: `FFMA R29, R12, R29, -0.5` -- so borderline points fall into the same bilinear cell as there),
 // range test of :288, corner tests of :56/:62/:68/:74.
-__device__ __forceinline__ PointGeo point_geometry(float loc_x, float loc_y, int H, int W, int level_base_bytes,
-                                                   int pixel_bytes) {
+__device__ __forceinline__ PointGeo point_geometry(float loc_x, float loc_y, int H, int W, int level_start,
+                                                   int pixel_units) {
     PointGeo g;
     const float fw = (float)W, fh = (float)H;
     const float x = fmaf(loc_x, fw, -0.5f);
     const float y = fmaf(loc_y, fh, -0.5f);
     const bool in_range = (y > -1.f) && (x > -1.f) && (y < fh) && (x < fw);   // false for NaN / inf
     const float xf = floorf(x), yf = floorf(y);
-    const int x0 = (int)xf, y0 = (int)yf;     // saturating conversion; clamped below when out of range
+    const int x0 = (int)xf, y0 = (int)yf;     // saturating conversion (NaN -> 0); clamped below
     g.lx = in_range ? x - xf : 0.f;
     g.ly = in_range ? y - yf : 0.f;
     const float hx = 1.f - g.lx, hy = 1.f - g.ly;
-    const bool xa = in_range && x0 >= 0, xb = in_range && x0 + 1 <= W - 1;
-    const bool ya = in_range && y0 >= 0, yb = in_range && y0 + 1 <= H - 1;
-    const int xs = min(max(x0, -1), W - 1), ys = min(max(y0, -1), H - 1);   // [-1, size-1]: no overflow below
-    const int xc0 = max(xs, 0), xc1 = min(xs + 1, W - 1), yc0 = max(ys, 0), yc1 = min(ys + 1, H - 1);
-    const int dx = (xc1 - xc0) * pixel_bytes;
-    g.o00 = level_base_bytes + (yc0 * W + xc0) * pixel_bytes;
-    g.o10 = level_base_bytes + (yc1 * W + xc0) * pixel_bytes;
-    g.o01 = g.o00 + dx;
-    g.o11 = g.o10 + dx;
+    const int xc0 = min(max(x0, 0), W - 1), yc0 = min(max(y0, 0), H - 1);
+    const int xc1 = min(max(x0, -1) + 1, W - 1), yc1 = min(max(y0, -1) + 1, H - 1);   // max first: no overflow at INT_MAX
+    const bool xa = in_range && x0 >= 0, xb = in_range && x0 < W - 1;
+    const bool ya = y0 >= 0, yb = y0 < H - 1;
+    const int r0 = level_start + yc0 * W, r1 = level_start + yc1 * W;
+    g.o00 = (uint32_t)((r0 + xc0) * pixel_units);
+    g.o01 = (uint32_t)((r0 + xc1) * pixel_units);
+    g.o10 = (uint32_t)((r1 + xc0) * pixel_units);
+    g.o11 = (uint32_t)((r1 + xc1) * pixel_units);
     g.w00 = (xa && ya) ? hy * hx : 0.f;
     g.w01 = (xb && ya) ? hy * g.lx : 0.f;
     g.w10 = (xa && yb) ? g.ly * hx : 0.f;
@@ -152,31 +231,10 @@ __device__ __forceinline__ PointGeo point_geometry(float loc_x, float loc_y, int
     return g;
 }
 
-// Which four queries (one per 8-lane group) a warp handles in pass `tile`, and whether they exist.
-struct QuerySel {
-    int q;
-    bool valid;
-};
-__device__ __forceinline__ QuerySel select_query(bool tiled, const Dims &d, const LevelTable &lt, int tile, int warp,
-                                                 int grp) {
-    QuerySel s;
-    if (tiled) {
-        int lv = 0;
-        while (lv + 1 < d.L && tile >= lt.tile_cum[lv + 1]) ++lv;
-        const int t = tile - lt.tile_cum[lv];
-        const int ty = t / lt.tiles_x[lv], tx = t - ty * lt.tiles_x[lv];
-        const int y = ty * kTile + (warp >> 1), x = tx * kTile + ((warp & 1) << 2) + grp;
-        s.valid = (y < lt.H[lv]) && (x < lt.W[lv]);
-        s.q = lt.start[lv] + y * lt.W[lv] + x;
-    } else {
-        s.q = tile * (kWarps * 4) + warp * 4 + grp;
-        s.valid = s.q < d.Lq;
-    }
-    return s;
-}
-
+template <int WARPS>
 __device__ __forceinline__ void load_level_table(LevelTable &lt, const int64_t *shapes, const int64_t *start, int L,
                                                  int Lq) {
+    constexpr int kTileW = Tile<WARPS>::W, kTileH = Tile<WARPS>::H;
     if (threadIdx.x < L) {
         lt.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
         lt.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
@@ -186,7 +244,7 @@ __device__ __forceinline__ void load_level_table(LevelTable &lt, const int64_t *
     if (threadIdx.x == 0) {
         int cum = 0, rows = 0, dense = 1;
         for (int l = 0; l < L; ++l) {
-            const int tx = (lt.W[l] + kTile - 1) / kTile, ty = (lt.H[l] + kTile - 1) / kTile;
+            const int tx = (lt.W[l] + kTileW - 1) / kTileW, ty = (lt.H[l] + kTileH - 1) / kTileH;
             lt.tiles_x[l] = tx;
             lt.tile_cum[l] = cum;
             cum += tx * ty;
@@ -199,246 +257,287 @@ __device__ __forceinline__ void load_level_table(LevelTable &lt, const int64_t *
     __syncthreads();
 }
 
-// Packed fp32 pairs: Blackwell's FFMA2 / FMUL2 do two lanes of fp32 math per issue slot, with a scalar
-// operand broadcast for free -- the kernels are issue-bound, so every row update is written in pairs.
-__device__ __forceinline__ float2 fma2s(float s, float2 v, float2 acc) { return __ffma2_rn(make_float2(s, s), v, acc); }
-__device__ __forceinline__ float2 mul2s(float s, float2 v) { return __fmul2_rn(make_float2(s, s), v); }
-struct Row {            // four channels as two pairs
-    float2 lo, hi;
-};
-template <typename VT> struct RowIO;
-template <> struct RowIO<float> {
-    static constexpr int kBytes = 16;          // bytes of four channels
-    static __device__ __forceinline__ Row load(const char *p) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
-        return Row{make_float2(v.x, v.y), make_float2(v.z, v.w)};
+// The query a lane group works on in pass `tile` of a frame.  Tiled walk (encoder, Lq == S and the levels
+// partition the queries): the tile is an 8 x 4 patch of one level's pixels, so the rows its 8 warps gather
+// overlap and stay in L1.  Linear walk otherwise: 32 consecutive queries.
+template <int WARPS>
+__device__ __forceinline__ int select_query(bool tiled, const Dims &d, const LevelTable &lt, int tile, int warp,
+                                            int grp) {
+    constexpr int kTileW = Tile<WARPS>::W, kTileH = Tile<WARPS>::H, kPerRow = Tile<WARPS>::kWarpsPerRow;
+    constexpr int kTaskQueries = Tile<WARPS>::kQueries;
+    if (tiled) {
+        int lv = 0;
+        while (lv + 1 < d.L && tile >= lt.tile_cum[lv + 1]) ++lv;
+        const int t = tile - lt.tile_cum[lv];
+        const int ty = t / lt.tiles_x[lv], tx = t - ty * lt.tiles_x[lv];
+        const int y = ty * kTileH + warp / kPerRow, x = tx * kTileW + ((warp % kPerRow) << 2) + grp;
+        return (y < lt.H[lv] && x < lt.W[lv]) ? lt.start[lv] + y * lt.W[lv] + x : -1;
     }
-    static __device__ __forceinline__ void store(char *p, Row r) {
-        *reinterpret_cast<float4 *>(p) = make_float4(r.lo.x, r.lo.y, r.hi.x, r.hi.y);
-    }
-};
-template <> struct RowIO<__nv_bfloat16> {
-    static constexpr int kBytes = 8;
-    static __device__ __forceinline__ Row load(const char *p) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p));
-        return Row{make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u)),
-                   make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u))};
-    }
-    static __device__ __forceinline__ void store(char *p, Row r) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(r.lo.x, r.lo.y), hi = __floats2bfloat162_rn(r.hi.x, r.hi.y);
-        uint2 raw;
-        raw.x = *reinterpret_cast<uint32_t *>(&lo);
-        raw.y = *reinterpret_cast<uint32_t *>(&hi);
-        *reinterpret_cast<uint2 *>(p) = raw;
+    const int q = tile * kTaskQueries + warp * 4 + grp;
+    return q < d.Lq ? q : -1;
+}
+
+// Persistent task walk shared by both kernels: worker `rank` of `workers` takes passes rank, rank + workers, ...
+// (the grid is exactly SMs x resident CTAs per SM: one wave).  A pass is (frame n, head m, tile).  Passes are
+// ordered so that the CTAs running at the same time work on DIFFERENT (frame, head) slices:
+//     frames are taken `fchunk` at a time (as many as keep their `value` slices in L2 together); inside a chunk
+//     the slice (frame, head) runs fastest, then the tile.
+// Why: the backward's reds into a coarse pyramid level (60 .. 720 rows per slice, a quarter of all reds each) are
+// serialised per address by the L2 atomic units -- 0.96 TB/s when every CTA hits the same 64 rows against
+// 6.4 TB/s when they are spread over 32k rows (profiles/r1_ubench_gather_b200_part3_hotspots.jsonl).
+struct TaskWalk {
+    int n, m, tile;        // current pass
+    uint32_t p, stride, total, tiles, M, N, fchunk;
+    __device__ __forceinline__ TaskWalk(int N_, int M_, int tiles_, int fchunk_, int rank, int workers)
+        : n(0), m(0), tile(0), p((uint32_t)rank), stride((uint32_t)workers), total((uint32_t)N_ * M_ * tiles_),
+          tiles((uint32_t)tiles_), M((uint32_t)M_), N((uint32_t)N_), fchunk((uint32_t)fchunk_) {}
+    // advance to the next pass; false when this worker is done
+    __device__ __forceinline__ bool next() {
+        if (p >= total) return false;
+        const uint32_t per_chunk = fchunk * M * tiles;
+        const uint32_t c = p / per_chunk, rem = p - c * per_chunk;
+        const uint32_t f0 = c * fchunk, frames = min(fchunk, N - f0);      // the last chunk may be short
+        const uint32_t slices = frames * M;
+        const uint32_t t = rem / slices, sl = rem - t * slices;
+        const uint32_t f = sl / M;
+        tile = (int)t;
+        n = (int)(f0 + f);
+        m = (int)(sl - f * M);
+        p += stride;
+        return true;
     }
 };
 
 // ------------------------------------------------------------------------------------------------
-// Tiled forward, D = 32.  grid: persistent, CTA b takes tasks b, b+grid, ... ; a task is
-// (frame n, query tile, head m), m fastest.  ROUNDS = ceil(L*P / 8); a round stages 8 points per lane
-// group (slots past L*P carry zero weights), then gathers them branch-free.
+// Tiled forward, D = 32.  ROUNDS = ceil(L*P / 8): lane `cl` of a group stages points cl, 8+cl, ... of the
+// group's query (slots past L*P carry zero weights), then every lane gathers all of them branch-free.
+//   per point and warp: 2 broadcast LDS.128 (weights, offsets) + 4 LDG.128 (four rows each) + 8 FFMA2.
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int ROUNDS>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+template <int ROUNDS, int WARPS> struct FwdSmem {
+    static constexpr int kSlots = ROUNDS * 8 + 1;   // +1: the four groups of a warp read four different banks
+    LevelTable lt;
+    float4 w[WARPS][4][kSlots];   // a*w00, a*w01, a*w10, a*w11
+    uint4 o[WARPS][4][kSlots];    // unit offsets of the four corners
+};
+extern __shared__ __align__(16) unsigned char msda_smem[];
+
+template <typename VT, int ROUNDS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
 msda_fwd_tiled(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ start,
                const float *__restrict__ loc, const float *__restrict__ attn, VT *__restrict__ out, Dims d) {
-    __shared__ LevelTable lt;
-    __shared__ float4 s_w[kWarps][4][kPad];   // a*w00, a*w01, a*w10, a*w11
-    __shared__ int4 s_o[kWarps][4][kPad];     // byte offsets of the four corners
-    load_level_table(lt, shapes, start, d.L, d.Lq);
+    using IO = RowIO<VT>;
+    using Vec = typename IO::Vec;
+    constexpr int kTaskQueries = Tile<WARPS>::kQueries;
+    FwdSmem<ROUNDS, WARPS> &sm = *reinterpret_cast<FwdSmem<ROUNDS, WARPS> *>(msda_smem);
+    LevelTable &lt = sm.lt;
+    auto &s_w = sm.w;
+    auto &s_o = sm.o;
+    load_level_table<WARPS>(lt, shapes, start, d.L, d.Lq);
     const bool tiled = d.tiled && lt.dense;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, cl = lane & 7;
     const int pts = d.L * d.P;
-    const int pixel_bytes = d.M * 32 * (int)sizeof(VT);
-    int lvl[ROUNDS];
+    const int pixel_units = d.M * 8;
+    uint32_t lv = 0;     // level of this lane's point in each round, one byte per round
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) lvl[r] = min((8 * r + cl) / d.P, d.L - 1);
+    for (int r = 0; r < ROUNDS; ++r) lv |= (uint32_t)min((8 * r + cl) / d.P, d.L - 1) << (8 * r);
 
-    const int tiles = tiled ? lt.tile_cum[d.L] : (d.Lq + kWarps * 4 - 1) / (kWarps * 4);
-    const int64_t total = (int64_t)d.N * tiles * d.M;
-    for (int64_t task = blockIdx.x; task < total; task += gridDim.x) {
-        const int m = (int)(task % d.M);
-        const int tile = (int)((task / d.M) % tiles);
-        const int64_t n = task / ((int64_t)d.M * tiles);
-        const QuerySel qs = select_query(tiled, d, lt, tile, warp, grp);
-        if (!__any_sync(0xffffffffu, qs.valid)) continue;
-        const int64_t row = (n * d.Lq + qs.q) * d.M + m;              // (n, q, m)
-        // frame n, head m, this lane's four channels
-        const char *vb = reinterpret_cast<const char *>(value) +
-                         ((n * d.S * d.M + m) * 32 + cl * 4) * (int64_t)sizeof(VT);
-        float2 acc_lo = make_float2(0.f, 0.f), acc_hi = make_float2(0.f, 0.f);
+    const int tiles = tiled ? lt.tile_cum[d.L] : (d.Lq + kTaskQueries - 1) / kTaskQueries;
+    for (TaskWalk t(d.N, d.M, tiles, d.fchunk, blockIdx.x, gridDim.x); t.next();) {
+        const int m = t.m;
+        const int q = select_query<WARPS>(tiled, d, lt, t.tile, warp, grp);
+        if (!__any_sync(0xffffffffu, q >= 0)) continue;
+        const int64_t row = ((int64_t)t.n * d.Lq + max(q, 0)) * d.M + m;           // (n, q, m)
+        // stage all points of the four queries
+        float2 xy[ROUNDS];
+        float a[ROUNDS];
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
-            const int pt = 8 * r + cl;
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            int4 o = make_int4(0, 0, 0, 0);
-            if (qs.valid && pt < pts) {
-                const float2 xy = ld_stream_f2(loc + (row * pts + pt) * 2);
-                const float a = ld_stream_f1(attn + row * pts + pt);
-                const int l = lvl[r];
-                const PointGeo g = point_geometry(xy.x, xy.y, lt.H[l], lt.W[l], lt.start[l] * pixel_bytes, pixel_bytes);
-                w = make_float4(a * g.w00, a * g.w01, a * g.w10, a * g.w11);
-                o = make_int4(g.o00, g.o01, g.o10, g.o11);
+            const bool on = q >= 0 && 8 * r + cl < pts;
+            xy[r] = make_float2(-4.f, -4.f);        // out of range: zero weights, offsets clamped in bounds
+            a[r] = 0.f;
+            if (on) {
+                xy[r] = ld_stream_f2(loc + (row * pts + 8 * r + cl) * 2);
+                a[r] = ld_stream_f1(attn + row * pts + 8 * r + cl);
             }
-            s_w[warp][grp][cl] = w;
-            s_o[warp][grp][cl] = o;
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const float4 pw = s_w[warp][grp][it];
-                const int4 po = s_o[warp][grp][it];
-                const Row v00 = RowIO<VT>::load(at(vb, po.x));
-                const Row v01 = RowIO<VT>::load(at(vb, po.y));
-                const Row v10 = RowIO<VT>::load(at(vb, po.z));
-                const Row v11 = RowIO<VT>::load(at(vb, po.w));
-                acc_lo = fma2s(pw.x, v00.lo, acc_lo); acc_hi = fma2s(pw.x, v00.hi, acc_hi);
-                acc_lo = fma2s(pw.y, v01.lo, acc_lo); acc_hi = fma2s(pw.y, v01.hi, acc_hi);
-                acc_lo = fma2s(pw.z, v10.lo, acc_lo); acc_hi = fma2s(pw.z, v10.hi, acc_hi);
-                acc_lo = fma2s(pw.w, v11.lo, acc_lo); acc_hi = fma2s(pw.w, v11.hi, acc_hi);
-            }
-            __syncwarp();
         }
-        if (qs.valid)
-            RowIO<VT>::store(reinterpret_cast<char *>(out) + (row * 32 + cl * 4) * (int64_t)sizeof(VT), Row{acc_lo, acc_hi});
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int l = (lv >> (8 * r)) & 0xff;
+            const PointGeo g = point_geometry(xy[r].x, xy[r].y, lt.H[l], lt.W[l], lt.start[l], pixel_units);
+            const float aa = g.valid ? a[r] : 0.f;      // an out-of-range point ignores its weight (cuh:288)
+            s_w[warp][grp][8 * r + cl] = make_float4(aa * g.w00, aa * g.w01, aa * g.w10, aa * g.w11);
+            s_o[warp][grp][8 * r + cl] = make_uint4(g.o00, g.o01, g.o10, g.o11);
+        }
+        __syncwarp();
+        // frame n, head m, this lane's four channels
+        const Vec *vb = reinterpret_cast<const Vec *>(value) + (((int64_t)t.n * d.S * d.M + m) * 8 + cl);
+        Row acc{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        // One LDG.128 per corner moves four rows (one per lane group).  What bounds this loop is the L1's request
+        // rate: 4.1 cycles for a four-row request that hits, 8.1 as soon as ONE row misses (measured,
+        // profiles/r1_ubench_gather_b200_part2.jsonl) -- deeper software pipelining / more registers per thread
+        // change nothing (tried: 64 .. 255 registers, 1 .. 16 points of loads in flight per warp).
+#pragma unroll
+        for (int it = 0; it < ROUNDS * 8; ++it) {
+            const float4 pw = s_w[warp][grp][it];
+            const uint4 po = s_o[warp][grp][it];
+            const Row v00 = IO::load(row_at(vb, po.x));
+            const Row v01 = IO::load(row_at(vb, po.y));
+            const Row v10 = IO::load(row_at(vb, po.z));
+            const Row v11 = IO::load(row_at(vb, po.w));
+            fma_row(pw.x, v00, acc);
+            fma_row(pw.y, v01, acc);
+            fma_row(pw.z, v10, acc);
+            fma_row(pw.w, v11, acc);
+        }
+        __syncwarp();
+        if (q >= 0) IO::store(reinterpret_cast<Vec *>(out) + (row * 8 + cl), acc);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Tiled backward, D = 32.  Same task walk as the forward.  grad_value (fp32) must be zero on entry.
 //
-// Per point and per lane (4 channels) the loop only forms the four corner dot products
+// Per point and per lane (4 channels) the gather loop forms the four corner dot products
 //     p_i = sum_c grad_out[c] * v_i[c]
-// and the scatter rows (a * w_i) * grad_out.  The 8-lane sums of p_i land, transposed, in the lane that
-// owns the point, which finishes with scalars (cuh:123-158 regrouped by corner):
+// and sends the scatter rows (a * w_i) * grad_out as predicated vector reds.  The partial p_i of the 8
+// lanes of a group are transposed through shared memory (one STS.128 per point, then the lane that
+// owns the point adds the 8 partials), and that lane finishes with scalars (cuh:123-158 regrouped by corner):
 //     grad_attn = sum_i w_i p_i
 //     grad_x    = W * a * ( hy (p01 - p00) + ly (p11 - p10) )      (invalid corners dropped)
 //     grad_y    = H * a * ( hx (p10 - p00) + lx (p11 - p01) )
 // ------------------------------------------------------------------------------------------------
-// Sum v[0..7] across the 8 lanes of a group so that lane `cl` ends with the total of v[cl]:
-// 7 shuffles instead of 24 for eight separate butterfly reductions.
-__device__ __forceinline__ float transpose_reduce8(const float (&v)[8], int cl) {
-    float u[4], t[2];
-    const bool b2 = cl & 4, b1 = cl & 2, b0 = cl & 1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float keep = b2 ? v[j + 4] : v[j], send = b2 ? v[j] : v[j + 4];
-        u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const float keep = b1 ? u[j + 2] : u[j], send = b1 ? u[j] : u[j + 2];
-        t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const float keep = b0 ? t[1] : t[0], send = b0 ? t[0] : t[1];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
+template <int WARPS> struct BwdSmem {
+    LevelTable lt;
+    float4 w[WARPS][4][9];      // a*w00, a*w01, a*w10, a*w11   (scatter weights), one round
+    uint4 o[WARPS][4][9];       // unit offsets of the four corners
+    float4 p[WARPS][4][8][8];   // [point][lane]: that lane's partial p00, p01, p10, p11
+    float4 own[WARPS][32][2];   // per lane: its own point's bilinear weights; lx, ly, attention, corner validity
+};
 
-__device__ __forceinline__ float dot4(const Row &a, const Row &b) {
-    const float2 t = __ffma2_rn(a.hi, b.hi, __fmul2_rn(a.lo, b.lo));
-    return t.x + t.y;
-}
-
-template <typename VT, int ROUNDS>
-__global__ void __launch_bounds__(kWarps * 32, 1)
+template <typename VT, int ROUNDS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
 msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ start, const float *__restrict__ loc, const float *__restrict__ attn,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d) {
-    __shared__ LevelTable lt;
-    __shared__ float4 s_w[kWarps][4][kPad];   // a*w00, a*w01, a*w10, a*w11   (scatter weights)
-    __shared__ int4 s_o[kWarps][4][kPad];     // byte offsets of the four corners
-    load_level_table(lt, shapes, start, d.L, d.Lq);
+    using IO = RowIO<VT>;
+    using Vec = typename IO::Vec;
+    constexpr int kTaskQueries = Tile<WARPS>::kQueries;
+    BwdSmem<WARPS> &sm = *reinterpret_cast<BwdSmem<WARPS> *>(msda_smem);
+    LevelTable &lt = sm.lt;
+    auto &s_w = sm.w;
+    auto &s_o = sm.o;
+    auto &s_p = sm.p;
+    auto &s_own = sm.own;
+    load_level_table<WARPS>(lt, shapes, start, d.L, d.Lq);
     const bool tiled = d.tiled && lt.dense;
-    constexpr int kGradScale = 4 / (int)sizeof(VT);   // grad_value is fp32: its byte offsets are this x value's
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, cl = lane & 7;
     const int pts = d.L * d.P;
-    const int pixel_bytes = d.M * 32 * (int)sizeof(VT);
-    int lvl[ROUNDS];
+    const int pixel_units = d.M * 8;
+    // Dims::bwd_mode (measurement only): 1 = gather / reduce without the scatter, 2 = the scatter alone (no `value`
+    // traffic at all).  Together they show what bounds the kernel: the scatter alone takes ~85 % of the full
+    // backward -- the L2 atomic units, chip-wide.  0 = the real thing.
+    const bool scatter = d.bwd_mode != 1 && !d.debug_skip_scatter, gather = d.bwd_mode != 2;
+    const int rank = blockIdx.x, workers = gridDim.x;
+    uint32_t lv = 0;     // level of this lane's point in each round, one byte per round
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) lvl[r] = min((8 * r + cl) / d.P, d.L - 1);
+    for (int r = 0; r < ROUNDS; ++r) lv |= (uint32_t)min((8 * r + cl) / d.P, d.L - 1) << (8 * r);
 
-    const int tiles = tiled ? lt.tile_cum[d.L] : (d.Lq + kWarps * 4 - 1) / (kWarps * 4);
-    const int64_t total = (int64_t)d.N * tiles * d.M;
-    for (int64_t task = blockIdx.x; task < total; task += gridDim.x) {
-        const int m = (int)(task % d.M);
-        const int tile = (int)((task / d.M) % tiles);
-        const int64_t n = task / ((int64_t)d.M * tiles);
-        const QuerySel qs = select_query(tiled, d, lt, tile, warp, grp);
-        if (!__any_sync(0xffffffffu, qs.valid)) continue;
-        const int64_t row = (n * d.Lq + qs.q) * d.M + m;
-        const int64_t slice = (n * d.S * d.M + m) * 32 + cl * 4;      // element offset of frame n, head m, 4 channels
-        const char *vb = reinterpret_cast<const char *>(value) + slice * (int64_t)sizeof(VT);
-        const char *gb = reinterpret_cast<const char *>(grad_value) + slice * 4;
+    const int tiles = tiled ? lt.tile_cum[d.L] : (d.Lq + kTaskQueries - 1) / kTaskQueries;
+    for (TaskWalk t(d.N, d.M, tiles, d.fchunk, rank, workers); t.next();) {
+        const int m = t.m;
+        const int q = select_query<WARPS>(tiled, d, lt, t.tile, warp, grp);
+        if (!__any_sync(0xffffffffu, q >= 0)) continue;
+        const int64_t row = ((int64_t)t.n * d.Lq + max(q, 0)) * d.M + m;
+        const int64_t slice = ((int64_t)t.n * d.S * d.M + m) * 8 + cl;      // unit offset of frame n, head m, this lane
+        const Vec *vb = reinterpret_cast<const Vec *>(value) + slice;
+        float4 *gb = reinterpret_cast<float4 *>(grad_value) + slice;
+        float2 xy[ROUNDS];
+        float a[ROUNDS];
         Row go{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        if (qs.valid) go = RowIO<VT>::load(reinterpret_cast<const char *>(grad_out) + (row * 32 + cl * 4) * (int64_t)sizeof(VT));
+        if (q >= 0) go = IO::load_stream(reinterpret_cast<const Vec *>(grad_out) + (row * 8 + cl));
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const bool on = q >= 0 && 8 * r + cl < pts;
+            xy[r] = make_float2(-4.f, -4.f);
+            a[r] = 0.f;
+            if (on) {
+                xy[r] = ld_stream_f2(loc + (row * pts + 8 * r + cl) * 2);
+                a[r] = ld_stream_f1(attn + row * pts + 8 * r + cl);
+            }
+        }
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int pt = 8 * r + cl;
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            int4 o = make_int4(0, 0, 0, 0);
-            PointGeo own;                                   // this lane's own point, kept for the epilogue
-            own.w00 = own.w01 = own.w10 = own.w11 = own.lx = own.ly = 0.f;
-            own.valid = 0;
-            float a_own = 0.f, fw_own = 0.f, fh_own = 0.f;
-            if (qs.valid && pt < pts) {
-                const float2 xy = ld_stream_f2(loc + (row * pts + pt) * 2);
-                a_own = ld_stream_f1(attn + row * pts + pt);
-                const int l = lvl[r];
-                own = point_geometry(xy.x, xy.y, lt.H[l], lt.W[l], lt.start[l] * pixel_bytes, pixel_bytes);
-                fw_own = (float)lt.W[l];
-                fh_own = (float)lt.H[l];
-                w = make_float4(a_own * own.w00, a_own * own.w01, a_own * own.w10, a_own * own.w11);
-                o = make_int4(own.o00, own.o01, own.o10, own.o11);
+            const int l = (lv >> (8 * r)) & 0xff;
+            {
+                const PointGeo g = point_geometry(xy[r].x, xy[r].y, lt.H[l], lt.W[l], lt.start[l], pixel_units);
+                const float aa = g.valid ? a[r] : 0.f;      // an out-of-range point ignores its weight (cuh:365)
+                s_w[warp][grp][cl] = make_float4(aa * g.w00, aa * g.w01, aa * g.w10, aa * g.w11);
+                s_o[warp][grp][cl] = make_uint4(g.o00, g.o01, g.o10, g.o11);
+                // what this lane needs again after the gather loop, parked in shared memory (registers are
+                // what bounds the loads in flight)
+                s_own[warp][lane][0] = make_float4(g.w00, g.w01, g.w10, g.w11);
+                s_own[warp][lane][1] = make_float4(g.lx, g.ly, aa, __int_as_float(g.valid));
             }
-            s_w[warp][grp][cl] = w;
-            s_o[warp][grp][cl] = o;
             __syncwarp();
-            float p00[8], p01[8], p10[8], p11[8];
+            if (!gather) {
+                // scatter-only role: grad_value[corner] += (a * w_corner) * grad_out       (cuh:125,134,143,152)
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const float4 pw = s_w[warp][grp][it];
+                    const uint4 po = s_o[warp][grp][it];
+                    red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
+                    red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
+                    red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
+                    red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
+                }
+                __syncwarp();
+                continue;
+            }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const float4 pw = s_w[warp][grp][it];
-                const int4 po = s_o[warp][grp][it];
-                const Row v00 = RowIO<VT>::load(at(vb, po.x));
-                const Row v01 = RowIO<VT>::load(at(vb, po.y));
-                const Row v10 = RowIO<VT>::load(at(vb, po.z));
-                const Row v11 = RowIO<VT>::load(at(vb, po.w));
-                p00[it] = dot4(go, v00);
-                p01[it] = dot4(go, v01);
-                p10[it] = dot4(go, v10);
-                p11[it] = dot4(go, v11);
-                // scatter: grad_value[corner] += (a * w_corner) * grad_out              (cuh:125,134,143,152)
-                // A point with no contributing corner (out of range, zero attention) is skipped as a whole;
-                // otherwise its clamped corners receive +0, which is harmless.
-                const uint32_t any_w = (__float_as_uint(pw.x) | __float_as_uint(pw.y) | __float_as_uint(pw.z) |
-                                        __float_as_uint(pw.w)) << 1;
-                if (any_w != 0u && !d.debug_skip_scatter) {
-                    red_add_row(at(gb, po.x * kGradScale), pw.x, go.lo, go.hi);
-                    red_add_row(at(gb, po.y * kGradScale), pw.y, go.lo, go.hi);
-                    red_add_row(at(gb, po.z * kGradScale), pw.z, go.lo, go.hi);
-                    red_add_row(at(gb, po.w * kGradScale), pw.w, go.lo, go.hi);
-                }
+                const uint4 po = s_o[warp][grp][it];
+                const Row v00 = IO::load(row_at(vb, po.x));
+                const Row v01 = IO::load(row_at(vb, po.y));
+                const Row v10 = IO::load(row_at(vb, po.z));
+                const Row v11 = IO::load(row_at(vb, po.w));
+                // scatter: grad_value[corner] += (a * w_corner) * grad_out                  (cuh:125,134,143,152)
+                red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
+                red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
+                red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
+                red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
+                s_p[warp][grp][it][cl] = make_float4(dot_row(go, v00), dot_row(go, v01), dot_row(go, v10), dot_row(go, v11));
             }
             __syncwarp();
-            float q00 = transpose_reduce8(p00, cl), q01 = transpose_reduce8(p01, cl);
-            float q10 = transpose_reduce8(p10, cl), q11 = transpose_reduce8(p11, cl);
-            if (qs.valid && pt < pts) {
+            // this lane owns point `pt`: add the 8 lanes' partials (rotated start: no bank conflicts)
+            float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 p = s_p[warp][grp][cl][(k + cl) & 7];
+                qs.x += p.x; qs.y += p.y; qs.z += p.z; qs.w += p.w;
+            }
+            if (q >= 0 && pt < pts) {
+                const float4 ow = s_own[warp][lane][0], og = s_own[warp][lane][1];
+                const float lx = og.x, ly = og.y, a_own = og.z;
+                const int valid = __float_as_int(og.w);
                 // clamped (invalid) corners carry someone else's row: drop them (zero padding, cuh:56-78)
-                q00 = (own.valid & 1) ? q00 : 0.f;
-                q01 = (own.valid & 2) ? q01 : 0.f;
-                q10 = (own.valid & 4) ? q10 : 0.f;
-                q11 = (own.valid & 8) ? q11 : 0.f;
-                const float hx = 1.f - own.lx, hy = 1.f - own.ly;
-                const float ga = own.w00 * q00 + own.w01 * q01 + own.w10 * q10 + own.w11 * q11;       // :156
-                const float gx = hy * (q01 - q00) + own.ly * (q11 - q10);                             // :157
-                const float gy = hx * (q10 - q00) + own.lx * (q11 - q01);                             // :158
+                const float q00 = (valid & 1) ? qs.x : 0.f, q01 = (valid & 2) ? qs.y : 0.f;
+                const float q10 = (valid & 4) ? qs.z : 0.f, q11 = (valid & 8) ? qs.w : 0.f;
+                const float hx = 1.f - lx, hy = 1.f - ly;
+                const float ga = ow.x * q00 + ow.y * q01 + ow.z * q10 + ow.w * q11;                   // :156
+                const float gx = hy * (q01 - q00) + ly * (q11 - q10);                                 // :157
+                const float gy = hx * (q10 - q00) + lx * (q11 - q01);                                 // :158
                 grad_attn[row * pts + pt] = ga;
                 *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) =
-                    make_float2(fw_own * a_own * gx, fh_own * a_own * gy);
+                    make_float2((float)lt.W[l] * a_own * gx, (float)lt.H[l] * a_own * gy);
             }
         }
+        __syncwarp();
     }
 }
 
@@ -574,8 +673,20 @@ msda_bwd_generic(const T *__restrict__ grad_out, const T *__restrict__ value, co
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-Dims make_dims(int N, int S, int M, int L, int Lq, int P) {
-    return Dims{N, S, M, L, Lq, P, (Lq == S && !g_force_linear.load()) ? 1 : 0, g_skip_scatter.load()};
+// frames worked on at the same time: as many as keep value (+ grad_value) slices of ~48 MB in the 126 MB L2
+int frame_chunk(int N, int S, int M, int D, int elem_bytes) {
+    const int k = g_unit.load();
+    if (k > 0) return k < N ? k : (N > 0 ? N : 1);
+    const int64_t frame_bytes = (int64_t)S * M * D * elem_bytes;
+    int64_t f = (48ll << 20) / (frame_bytes > 0 ? frame_bytes : 1);
+    if (f < 1) f = 1;
+    if (f > N) f = N;
+    return (int)(f > 0 ? f : 1);
+}
+
+Dims make_dims(int N, int S, int M, int D, int L, int Lq, int P, int elem_bytes) {
+    return Dims{N, S, M, L, Lq, P, (Lq == S && !g_force_linear.load()) ? 1 : 0, g_skip_scatter.load(),
+                frame_chunk(N, S, M, D, elem_bytes), g_bwd_mode.load()};
 }
 
 bool tiled_ok(int channels, int L, int P) {
@@ -592,6 +703,14 @@ int check_dims(int N, int S, int M, int D, int L, int Lq, int P) {
 
 bool misaligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
+// grid = (slots, M): enough CTAs for `ctas_per_sm` residents on every SM, split over the heads
+constexpr int kDefaultFwdWarps = 16, kDefaultBwdWarps = 8;    // measured best on the A2D / YTVOS encoder shapes
+int warps_for(const std::atomic<int> &knob, int dflt) {
+    const int k = knob.load();
+    return (k == 8 || k == 16) ? k : dflt;
+}
+
+// exactly one wave: SMs x resident CTAs per SM
 int grid_for(int ctas_per_sm_default, const std::atomic<int> &knob) {
     const int k = knob.load();
     return sm_count() * (k > 0 ? k : ctas_per_sm_default);
@@ -603,32 +722,73 @@ int after_launch(const char *what) {
     return e == cudaSuccess ? MSDA_OK : fail_cuda(e, what);
 }
 
+template <typename K>
+int configure(K kernel, size_t smem) {
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    }
+    return MSDA_OK;
+}
+
+template <typename VT, int ROUNDS, int WARPS>
+int launch_fwd_one(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
+                   VT *out, const Dims &d, cudaStream_t st) {
+    const size_t smem = sizeof(FwdSmem<ROUNDS, WARPS>);
+    if (const int rc = configure(msda_fwd_tiled<VT, ROUNDS, WARPS>, smem)) return rc;
+    const int grid = grid_for(32 / WARPS, g_fwd_ctas_per_sm);
+    msda_fwd_tiled<VT, ROUNDS, WARPS><<<grid, WARPS * 32, smem, st>>>(value, shapes, start, loc, attn, out, d);
+    return after_launch("msda_fwd_tiled");
+}
+
+template <typename VT, int ROUNDS>
+int launch_fwd_rounds(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
+                      VT *out, const Dims &d, cudaStream_t st) {
+    switch (warps_for(g_fwd_warps, kDefaultFwdWarps)) {
+        case 8: return launch_fwd_one<VT, ROUNDS, 8>(value, shapes, start, loc, attn, out, d, st);
+        default: return launch_fwd_one<VT, ROUNDS, 16>(value, shapes, start, loc, attn, out, d, st);
+    }
+}
+
 template <typename VT>
 int launch_fwd_tiled(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
                      VT *out, const Dims &d, cudaStream_t st) {
-    const int rounds = (d.L * d.P + 7) / 8;
-    const int grid = grid_for(2, g_fwd_ctas_per_sm);
-    switch (rounds) {
-        case 1: msda_fwd_tiled<VT, 1><<<grid, kWarps * 32, 0, st>>>(value, shapes, start, loc, attn, out, d); break;
-        case 2: msda_fwd_tiled<VT, 2><<<grid, kWarps * 32, 0, st>>>(value, shapes, start, loc, attn, out, d); break;
-        case 3: msda_fwd_tiled<VT, 3><<<grid, kWarps * 32, 0, st>>>(value, shapes, start, loc, attn, out, d); break;
-        default: msda_fwd_tiled<VT, 4><<<grid, kWarps * 32, 0, st>>>(value, shapes, start, loc, attn, out, d); break;
+    switch ((d.L * d.P + 7) / 8) {
+        case 1: return launch_fwd_rounds<VT, 1>(value, shapes, start, loc, attn, out, d, st);
+        case 2: return launch_fwd_rounds<VT, 2>(value, shapes, start, loc, attn, out, d, st);
+        case 3: return launch_fwd_rounds<VT, 3>(value, shapes, start, loc, attn, out, d, st);
+        default: return launch_fwd_rounds<VT, 4>(value, shapes, start, loc, attn, out, d, st);
     }
-    return after_launch("msda_fwd_tiled");
+}
+
+template <typename VT, int ROUNDS, int WARPS>
+int launch_bwd_one(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
+                   const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st) {
+    const size_t smem = sizeof(BwdSmem<WARPS>);
+    if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS>, smem)) return rc;
+    const int grid = grid_for(32 / WARPS, g_bwd_ctas_per_sm);
+    msda_bwd_tiled<VT, ROUNDS, WARPS><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d);
+    return after_launch("msda_bwd_tiled");
+}
+
+template <typename VT, int ROUNDS>
+int launch_bwd_rounds(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
+                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st) {
+    switch (warps_for(g_bwd_warps, kDefaultBwdWarps)) {
+        case 8: return launch_bwd_one<VT, ROUNDS, 8>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+        default: return launch_bwd_one<VT, ROUNDS, 16>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+    }
 }
 
 template <typename VT>
 int launch_bwd_tiled(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st) {
-    const int rounds = (d.L * d.P + 7) / 8;
-    const int grid = grid_for(1, g_bwd_ctas_per_sm);
-    switch (rounds) {
-        case 1: msda_bwd_tiled<VT, 1><<<grid, kWarps * 32, 0, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d); break;
-        case 2: msda_bwd_tiled<VT, 2><<<grid, kWarps * 32, 0, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d); break;
-        case 3: msda_bwd_tiled<VT, 3><<<grid, kWarps * 32, 0, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d); break;
-        default: msda_bwd_tiled<VT, 4><<<grid, kWarps * 32, 0, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d); break;
+    switch ((d.L * d.P + 7) / 8) {
+        case 1: return launch_bwd_rounds<VT, 1>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+        case 2: return launch_bwd_rounds<VT, 2>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+        case 3: return launch_bwd_rounds<VT, 3>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+        default: return launch_bwd_rounds<VT, 4>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
     }
-    return after_launch("msda_bwd_tiled");
 }
 
 template <typename T>
@@ -655,7 +815,7 @@ int forward_any(const T *value, const int64_t *shapes, const int64_t *start, con
     if (const int rc = check_dims(N, S, M, D, L, Lq, P)) return rc;
     if ((int64_t)N * Lq == 0) return MSDA_OK;
     if (!value || !shapes || !start || !loc || !attn || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward: null pointer");
-    const Dims d = make_dims(N, S, M, L, Lq, P);
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, (int)sizeof(T));
     return forward_generic<T>(value, shapes, start, loc, attn, out, d, D, (cudaStream_t)stream);
 }
 
@@ -679,6 +839,10 @@ int msda_set_option(const char *key, int value) {
     if (!key) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_set_option: null key");
     if (!strcmp(key, "fwd_ctas_per_sm")) { g_fwd_ctas_per_sm = value; return MSDA_OK; }
     if (!strcmp(key, "bwd_ctas_per_sm")) { g_bwd_ctas_per_sm = value; return MSDA_OK; }
+    if (!strcmp(key, "bwd_mode")) { g_bwd_mode = value; return MSDA_OK; }
+    if (!strcmp(key, "frame_chunk")) { g_unit = value; return MSDA_OK; }
+    if (!strcmp(key, "fwd_warps")) { g_fwd_warps = value; return MSDA_OK; }
+    if (!strcmp(key, "bwd_warps")) { g_bwd_warps = value; return MSDA_OK; }
     if (!strcmp(key, "force_generic")) { g_force_generic = value; return MSDA_OK; }
     if (!strcmp(key, "force_linear_walk")) { g_force_linear = value; return MSDA_OK; }
     if (!strcmp(key, "debug_skip_scatter")) { g_skip_scatter = value; return MSDA_OK; }
@@ -694,7 +858,7 @@ int msda_forward_f32(const float *value, const int64_t *shapes, const int64_t *s
     if (!value || !shapes || !start || !loc || !attn || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward_f32: null pointer");
     if (misaligned(value, 16) || misaligned(out, 16) || misaligned(loc, 8))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward_f32: value/output must be 16-byte aligned, sampling_loc 8-byte aligned");
-    const Dims d = make_dims(N, S, M, L, Lq, P);
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, 4);
     return launch_fwd_tiled<float>(value, shapes, start, loc, attn, out, d, (cudaStream_t)stream);
 }
 
@@ -711,7 +875,7 @@ int msda_backward_f32(const float *go, const float *value, const int64_t *shapes
     if ((int64_t)N * Lq == 0) return MSDA_OK;
     if (!go || !value || !shapes || !start || !loc || !attn || !gl || !ga)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_f32: null pointer");
-    const Dims d = make_dims(N, S, M, L, Lq, P);
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, 4);
     if (!tiled_ok(D, L, P)) return backward_generic<float>(go, value, shapes, start, loc, attn, gv, gl, ga, d, D, st);
     if (misaligned(value, 16) || misaligned(go, 16) || misaligned(gv, 16) || misaligned(loc, 8) || misaligned(gl, 8))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_f32: value/grad_output/grad_value must be 16-byte aligned, loc tensors 8-byte aligned");
@@ -737,7 +901,7 @@ int msda_backward_f64(const double *go, const double *value, const int64_t *shap
     if ((int64_t)N * Lq == 0) return MSDA_OK;
     if (!go || !value || !shapes || !start || !loc || !attn || !gl || !ga)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_f64: null pointer");
-    const Dims d = make_dims(N, S, M, L, Lq, P);
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, 8);
     return backward_generic<double>(go, value, shapes, start, loc, attn, gv, gl, ga, d, D, st);
 }
 
@@ -751,7 +915,7 @@ int msda_forward_bf16(const uint16_t *value, const int64_t *shapes, const int64_
     if (!value || !shapes || !start || !loc || !attn || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward_bf16: null pointer");
     if (misaligned(value, 8) || misaligned(out, 8) || misaligned(loc, 8))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_forward_bf16: value/output/sampling_loc must be 8-byte aligned");
-    const Dims d = make_dims(N, S, M, L, Lq, P);
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, 2);
     return launch_fwd_tiled<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(value), shapes, start, loc, attn,
                                            reinterpret_cast<__nv_bfloat16 *>(out), d, (cudaStream_t)stream);
 }
@@ -774,7 +938,7 @@ int msda_backward_bf16(const uint16_t *go, const uint16_t *value, const int64_t 
             return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: null pointer");
         if (misaligned(value, 8) || misaligned(go, 8) || misaligned(gv32, 16) || misaligned(loc, 8) || misaligned(gl, 8))
             return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: misaligned pointer");
-        const Dims d = make_dims(N, S, M, L, Lq, P);
+        const Dims d = make_dims(N, S, M, D, L, Lq, P, 2);
         if (const int rc = launch_bwd_tiled<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(go),
                                                            reinterpret_cast<const __nv_bfloat16 *>(value), shapes, start,
                                                            loc, attn, gv32, gl, ga, d, st))

@@ -29,7 +29,7 @@ __device__ __forceinline__ uint32_t lcg(uint32_t &s) {
     return s >> 8;
 }
 
-enum Mode { LDG128 = 0, LDG256 = 1, LDG32 = 2, LDS128 = 3, RED128 = 4, RED32 = 5, LDG128_NC = 6 };
+enum Mode { LDG128 = 0, LDG256 = 1, LDG32 = 2, LDS128 = 3, RED128 = 4, RED32 = 5, LDG128_NC = 6, LDG64 = 7, ST128 = 8, RED64 = 9 };
 
 // window_rows: power of two.  shared_window: 0 -> each CTA has its own window (L1-resident when small),
 // 1 -> all CTAs draw from the same window of window_rows rows (L2).
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kThreads) bench(float *buf, int window_rows, i
     int grp, sub_bytes;
     if (MODE == LDG256) { grp = lane >> 2; sub_bytes = (lane & 3) * 32; }
     else if (MODE == LDG32 || MODE == RED32) { grp = 0; sub_bytes = lane * 4; }
+    else if (MODE == LDG64 || MODE == RED64) { grp = lane >> 4; sub_bytes = (lane & 15) * 8; }
     else { grp = lane >> 3; sub_bytes = (lane & 7) * 16; }
     uint32_t seed = (warp_global * 8 + grp) * 2654435761u + 12345u;
     if (MODE == LDS128) {
@@ -71,6 +72,13 @@ __global__ void __launch_bounds__(kThreads) bench(float *buf, int window_rows, i
                 asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                              : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g), "=f"(h) : "l"(base + off[u]));
                 acc.x += a + e; acc.y += b + f; acc.z += c + g; acc.w += d + h;
+            } else if (MODE == LDG64) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(base + off[u]));
+                acc.x += v.x; acc.y += v.y;
+            } else if (MODE == ST128) {
+                *reinterpret_cast<float4 *>(base + off[u]) = make_float4(1.f, 2.f, 3.f, (float)it);
+            } else if (MODE == RED64) {
+                asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1,%2};" :: "l"(base + off[u]), "f"(1.f), "f"(2.f) : "memory");
             } else if (MODE == LDG32) {
                 acc.x += __ldg(reinterpret_cast<const float *>(base + off[u]));
             } else if (MODE == LDS128) {
@@ -87,6 +95,71 @@ __global__ void __launch_bounds__(kThreads) bench(float *buf, int window_rows, i
     const long long t1 = clock64();
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
     if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;
+}
+
+// LDG.128, 4 rows per warp instruction, of which `n_far` rows come from the big shared (L2) window and the rest from
+// the CTA's private L1-resident window: what does ONE missing row cost a request?
+__global__ void __launch_bounds__(kThreads) bench_mixed(float *buf, int near_rows, int far_rows, int n_far, int iters,
+                                                        float *sink, long long *cycles) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int grp = lane >> 3, sub_bytes = (lane & 7) * 16;
+    // private windows live after the far window
+    char *far_base = reinterpret_cast<char *>(buf);
+    char *near_base = far_base + (size_t)far_rows * 128 + (size_t)blockIdx.x * near_rows * 128;
+    const bool far = grp < n_far;
+    char *base = far ? far_base : near_base;
+    const uint32_t mask = (far ? far_rows : near_rows) - 1;
+    uint32_t seed = (warp_global * 8 + grp) * 2654435761u + 12345u;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // warm the private window
+    for (int i = threadIdx.x; i < near_rows * 8; i += kThreads) acc.x += __ldg(reinterpret_cast<const float4 *>(near_base) + i).x;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        uint32_t off[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) off[u] = (lcg(seed) & mask) * 128u + sub_bytes;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(base + off[u]));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;
+}
+
+void run_mixed(float *buf, int n_far, int ctas_per_sm, int iters, int sms, float *sink, long long *d_cycles) {
+    const int grid = sms * ctas_per_sm;
+    const int near_rows = 128, far_rows = 1 << 17;
+    float best = 1e30f;
+    long long cyc_max = 0;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        bench_mixed<<<grid, kThreads>>>(buf, near_rows, far_rows, n_far, iters, sink, d_cycles);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) {
+            best = ms;
+            long long *h = (long long *)malloc(sizeof(long long) * grid);
+            CK(cudaMemcpy(h, d_cycles, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+            cyc_max = 0;
+            for (int i = 0; i < grid; ++i) cyc_max = h[i] > cyc_max ? h[i] : cyc_max;
+            free(h);
+        }
+    }
+    const double instr_per_sm = (double)ctas_per_sm * (kThreads / 32) * iters * kUnroll;
+    printf("{\"case\": \"ldg128_mixed\", \"rows_from_L2_of_4\": %d, \"warps_per_sm\": %d, \"ms\": %.4f, \"cycles_cta_max\": %lld, "
+           "\"cycles_per_row_per_sm\": %.3f, \"cycles_per_instr_per_sm\": %.3f}\n",
+           n_far, ctas_per_sm * kThreads / 32, best, cyc_max, cyc_max / (instr_per_sm * 4), cyc_max / instr_per_sm);
+    fflush(stdout);
 }
 
 template <int MODE>
@@ -117,7 +190,7 @@ void run(const char *name, float *buf, size_t buf_bytes, int window_rows, int sh
             free(h);
         }
     }
-    const int rows_per_instr = MODE == LDG256 ? 8 : (MODE == LDG32 || MODE == RED32) ? 1 : 4;
+    const int rows_per_instr = MODE == LDG256 ? 8 : (MODE == LDG32 || MODE == RED32) ? 1 : (MODE == LDG64 || MODE == RED64) ? 2 : 4;
     const double instr_per_sm = (double)ctas_per_sm * (kThreads / 32) * iters * kUnroll;
     const double rows_per_sm = instr_per_sm * rows_per_instr;
     const double bytes = rows_per_sm * sms * 128.0;
@@ -139,22 +212,39 @@ int main() {
     CK(cudaMalloc(&sink, 16));
     CK(cudaMalloc(&d_cycles, sizeof(long long) * sms * 32));
     const int iters = 400;
+    if (getenv("UBENCH_FULL")) {
     for (int cps : {2, 4, 8}) {
-        // L1-resident private window: 256 rows = 32 KB per CTA
         run<LDG128>("ldg128_4rows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "private 16 KB window per CTA");
         run<LDG256>("ldg256_8rows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "private 16 KB window per CTA");
         run<LDG32>("ldg32_1row_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "private 16 KB window per CTA");
         run<LDS128>("lds128_4rows", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "16 KB of shared memory per CTA");
-        // L2-resident shared window: 192k rows = 24 MB (one A2D value tensor)
         run<LDG128>("ldg128_4rows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "shared 16 MB window (L2)");
         run<LDG128_NC>("ldg128nc_4rows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "shared 16 MB window (L2), L1::no_allocate");
         run<LDG256>("ldg256_8rows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "shared 16 MB window (L2)");
         run<LDG32>("ldg32_1row_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "shared 16 MB window (L2)");
-        // reds: private small window (same L2 lines hit over and over), shared 16 MB window, 512 MB window (HBM)
         run<RED128>("red128_4rows_win", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "private 16 KB window per CTA");
         run<RED128>("red128_4rows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "shared 16 MB window (L2)");
         run<RED32>("red32_1row_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "shared 16 MB window (L2)");
         run<RED128>("red128_4rows_HBM", buf, buf_bytes, 1 << 22, 1, cps, iters, sms, sink, d_cycles, "shared 512 MB window (> L2)");
+    }
+    }
+    // second series: what a partially missing request costs; narrower requests; stores; reds on part of the chip
+    for (int cps : {4, 8}) {
+        if (getenv("UBENCH_HOT")) break;
+        for (int n_far = 0; n_far <= 4; ++n_far) run_mixed(buf, n_far, cps, iters, sms, sink, d_cycles);
+        run<LDG64>("ldg64_2rows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "16 lanes x 8 B per row, private window");
+        run<LDG64>("ldg64_2rows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "16 lanes x 8 B per row, shared 16 MB window");
+        run<ST128>("st128_4rows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "plain stores, shared 16 MB window");
+        run<RED64>("red64_2halfrows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "red.v2.f32: two 128 B rows per instruction");
+    }
+    // hot spots: every CTA reds into the SAME few rows (a coarse pyramid level has 60 .. 720 rows per head)
+    for (int rows : {64, 512, 4096, 32768})
+        run<RED128>("red128_4rows_hot", buf, buf_bytes, rows, 1, 4, iters, sms, sink, d_cycles, "all CTAs share this many rows");
+    for (int part : {37, 74, 111}) {
+        char note[64];
+        snprintf(note, sizeof(note), "only %d of %d SMs issue reds", part, sms);
+        run<RED128>("red128_4rows_L2_partial", buf, buf_bytes, 1 << 17, 1, 4, iters, part, sink, d_cycles, note);
+        run<LDG128>("ldg128_4rows_L2_partial", buf, buf_bytes, 1 << 17, 1, 4, iters, part, sink, d_cycles, note);
     }
     return 0;
 }
