@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 
 #define MSDA_OK 0
 #define MSDA_ERR_INVALID_ARGUMENT (-1) /* null pointer, non-positive dimension, misaligned pointer */
@@ -101,6 +101,49 @@ int msda_backward_bf16(const uint16_t *grad_output, const uint16_t *value, const
                        int num_query, int num_point,
                        float *grad_value_f32, uint16_t *grad_value_bf16,
                        float *grad_sampling_loc, float *grad_attn_weight, msda_stream_t stream);
+
+/* ---- fused module path (new).  Folds the elementwise work that
+ *      MSDeformAttn.forward does around the operator into the kernels (models/ops/modules/ms_deform_attn.py):
+ *        attention_weights  = softmax(logits) over the num_levels*num_point entries of a (query, head)   :101-102
+ *        sampling_locations = ref + offsets / (W_l, H_l)                     (ref_dim == 2)             :104-107
+ *                           = ref_xy + offsets / num_point * ref_wh * 0.5    (ref_dim == 4)             :108-110
+ *      offsets   [batch][num_query][num_heads][num_levels][num_point][2]   raw output of the sampling_offsets Linear
+ *      logits    [batch][num_query][num_heads][num_levels*num_point]       raw output of the attention_weights Linear
+ *      ref       [batch][num_query][num_levels][ref_dim]                   reference points (2) or boxes (4)
+ *      Forward: sampling_loc_out / attn_weight_out are optional (NULL = not materialised; the encoder discards
+ *      them, deformable_transformer.py:251; the decoder reads them, :365-375).
+ *      Backward: writes grad_value (zero-filled by the call), grad_offsets, grad_logits (softmax gradient
+ *      applied) and, if grad_sampling_loc_out is non-NULL, d/d sampling_locations, which the caller reduces over
+ *      heads and points into grad_reference_points when those need a gradient.
+ *      Shapes as msda_kernel_plan() == 1 only (channels == 32 ...): MSDA_ERR_UNSUPPORTED otherwise -- the caller
+ *      then uses the unfused operator above. ---- */
+int msda_fused_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                           const float *offsets, const float *logits, const float *ref, int ref_dim,
+                           int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                           int num_query, int num_point, float *output,
+                           float *sampling_loc_out, float *attn_weight_out, msda_stream_t stream);
+
+int msda_fused_backward_f32(const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const float *offsets, const float *logits,
+                            const float *ref, int ref_dim,
+                            int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                            int num_query, int num_point,
+                            float *grad_value, float *grad_offsets, float *grad_logits,
+                            float *grad_sampling_loc_out, msda_stream_t stream);
+
+int msda_fused_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const float *offsets, const float *logits, const float *ref, int ref_dim,
+                            int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                            int num_query, int num_point, uint16_t *output,
+                            float *sampling_loc_out, float *attn_weight_out, msda_stream_t stream);
+
+int msda_fused_backward_bf16(const uint16_t *grad_output, const uint16_t *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *offsets, const float *logits,
+                             const float *ref, int ref_dim,
+                             int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                             int num_query, int num_point,
+                             float *grad_value_f32, uint16_t *grad_value_bf16, float *grad_offsets, float *grad_logits,
+                             float *grad_sampling_loc_out, msda_stream_t stream);
 
 /* Which kernel a call with these dimensions runs: 1 = the sm_100a tiled kernel (channels == 32,
  * num_levels <= 16, num_levels*num_point <= 32), 0 = the generic kernel (any shape).  For tests and

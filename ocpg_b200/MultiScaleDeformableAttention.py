@@ -76,6 +76,46 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream                        # cu:65: current stream
 
 
+# Optional device timing of the library calls inside a larger program (bench: the operator's share of an
+# encoder step).  start_timing() .. stop_timing() brackets every C call with CUDA events on its stream.
+_TIMINGS = None
+
+
+class _Timed:
+    def __init__(self, kind, device):
+        self.kind, self.device = kind, device
+
+    def __enter__(self):
+        if _TIMINGS is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMINGS is not None and exc[0] is None:
+            self.b.record(torch.cuda.current_stream(self.device))
+            _TIMINGS.append((self.kind, self.a, self.b))
+        return False
+
+
+def start_timing():
+    global _TIMINGS
+    _TIMINGS = []
+
+
+def stop_timing():
+    """-> {kind: (calls, total_ms)} for kind in forward / backward (synchronises)."""
+    global _TIMINGS
+    rec, _TIMINGS = _TIMINGS or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, a, b in rec:
+        n, ms = out.get(kind, (0, 0.0))
+        out[kind] = (n + 1, ms + a.elapsed_time(b))
+    return out
+
+
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                            im2col_step: int) -> torch.Tensor:
     named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
@@ -85,7 +125,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     if int(im2col_step) <= 0:
         raise RuntimeError("im2col_step must be positive")
     sfx = _dtype_suffix(value, sampling_loc, attn_weight)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Timed("forward", value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)   # fully overwritten
         rc = getattr(_lib.lib(), f"msda_forward_{sfx}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
@@ -105,7 +145,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
         raise RuntimeError("grad_output must have value's dtype and N*Lq*M*D elements")
     sfx = _dtype_suffix(value, sampling_loc, attn_weight)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Timed("backward", value.device):
         grad_loc = torch.empty_like(sampling_loc)      # every element is written by the kernel
         grad_attn = torch.empty_like(attn_weight)
         st = _stream(value.device)
@@ -125,3 +165,88 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
                 grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), st)
     _lib.check(rc, "ms_deform_attn_backward")
     return [grad_value, grad_loc, grad_attn]
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused module path (not in the reference extension): softmax of the logits and the
+# reference-point / offset arithmetic of MSDeformAttn.forward (ms_deform_attn.py:100-110) run inside
+# the kernels.  Same checks and error behaviour as above.
+# ------------------------------------------------------------------------------------------------
+def fused_supported(value, n_levels: int, n_points: int) -> bool:
+    """True if the fused kernels cover this layout (the tiled sm_100a kernels: 32 channels per head ...)."""
+    if value.dtype not in (torch.float32, torch.bfloat16) or value.dim() != 4:
+        return False
+    return _lib.lib().msda_kernel_plan(value.element_size(), value.shape[2], value.shape[3], n_levels, n_points) == 1
+
+
+def _fused_dims(value, spatial_shapes, level_start_index, offsets, logits, ref):
+    if offsets.dim() != 6 or logits.dim() != 4 or ref.dim() != 4:
+        raise RuntimeError("offsets must be (N, Lq, M, L, P, 2), logits (N, Lq, M, L*P), reference_points (N, Lq, L, 2|4)")
+    N, Lq, M_, L_, P, _ = offsets.shape
+    attn_like = logits.view(N, Lq, M_, L_, P) if logits.shape == (N, Lq, M_, L_ * P) else logits
+    dims = _dims(value, spatial_shapes, level_start_index, offsets, attn_like)
+    ref_dim = ref.shape[-1]
+    if ref.shape != (N, Lq, L_, ref_dim) or ref_dim not in (2, 4):
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(ref_dim))  # :112-113
+    for name, t in (("offsets", offsets), ("logits", logits), ("reference_points", ref)):
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be float32")
+    return dims + (ref_dim,)
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, reference_points,
+                                 im2col_step: int, emit: bool = True):
+    """-> (output, sampling_locations | None, attention_weights | None)."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("offsets", offsets), ("logits", logits), ("reference_points", reference_points)]
+    _check_inputs(named, value)
+    N, S, M, D, L, Lq, P, ref_dim = _fused_dims(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
+    if int(im2col_step) <= 0:
+        raise RuntimeError("im2col_step must be positive")
+    sfx = {torch.float32: "f32", torch.bfloat16: "bf16"}.get(value.dtype)
+    if sfx is None:
+        raise RuntimeError(f"fused path: unsupported value dtype {value.dtype}")
+    with torch.cuda.device(value.device), _Timed("forward", value.device):
+        output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        loc = torch.empty_like(offsets) if emit else None
+        attn = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device) if emit else None
+        rc = getattr(_lib.lib(), f"msda_fused_forward_{sfx}")(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), offsets.data_ptr(),
+            logits.data_ptr(), reference_points.data_ptr(), ref_dim, N, S, M, D, L, Lq, P, output.data_ptr(),
+            loc.data_ptr() if emit else None, attn.data_ptr() if emit else None, _stream(value.device))
+    _lib.check(rc, "ms_deform_attn_fused_forward")
+    return output, loc, attn
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, offsets, logits, reference_points,
+                                  grad_output, im2col_step: int, need_grad_loc: bool = False):
+    """-> [grad_value, grad_offsets, grad_logits, grad_sampling_locations | None]."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("offsets", offsets), ("logits", logits), ("reference_points", reference_points),
+             ("grad_output", grad_output)]
+    _check_inputs(named, value)
+    N, S, M, D, L, Lq, P, ref_dim = _fused_dims(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
+    if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError("grad_output must have value's dtype and N*Lq*M*D elements")
+    sfx = {torch.float32: "f32", torch.bfloat16: "bf16"}.get(value.dtype)
+    if sfx is None:
+        raise RuntimeError(f"fused path: unsupported value dtype {value.dtype}")
+    with torch.cuda.device(value.device), _Timed("backward", value.device):
+        g_off = torch.empty_like(offsets)
+        g_logits = torch.empty_like(logits)
+        g_loc = torch.empty_like(offsets) if need_grad_loc else None
+        g_loc_ptr = g_loc.data_ptr() if need_grad_loc else None
+        st = _stream(value.device)
+        L_ = _lib.lib()
+        common = (grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                  offsets.data_ptr(), logits.data_ptr(), reference_points.data_ptr(), ref_dim, N, S, M, D, L, Lq, P)
+        grad_value = torch.empty_like(value)
+        if sfx == "bf16":
+            acc = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+            rc = L_.msda_fused_backward_bf16(*common, acc.data_ptr(), grad_value.data_ptr(), g_off.data_ptr(),
+                                             g_logits.data_ptr(), g_loc_ptr, st)
+        else:
+            rc = L_.msda_fused_backward_f32(*common, grad_value.data_ptr(), g_off.data_ptr(), g_logits.data_ptr(),
+                                            g_loc_ptr, st)
+    _lib.check(rc, "ms_deform_attn_fused_backward")
+    return [grad_value, g_off, g_logits, g_loc]

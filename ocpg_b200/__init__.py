@@ -9,8 +9,8 @@ Python/PyTorch host code calls hand-written CUDA kernels through the C ABI of in
 (ctypes); no Triton, no multi-backend dispatch, no CPU fallback.
 """
 from ._lib import build, lib, launch_count, set_option, LIB_PATH  # noqa: F401
-from .functions import MSDeformAttnFunction  # noqa: F401
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction  # noqa: F401
 from .modules import MSDeformAttn  # noqa: F401
 from . import MultiScaleDeformableAttention  # noqa: F401
 
-__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MultiScaleDeformableAttention", "build", "lib"]
+__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention", "build", "lib"]

@@ -25,7 +25,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 SYMBOLS = [
     "msda_abi_version", "msda_last_error", "msda_forward_f32", "msda_backward_f32", "msda_forward_f64",
     "msda_backward_f64", "msda_forward_bf16", "msda_backward_bf16", "msda_kernel_plan", "msda_launch_count",
-    "msda_set_option",
+    "msda_set_option", "msda_fused_forward_f32", "msda_fused_backward_f32", "msda_fused_forward_bf16",
+    "msda_fused_backward_bf16",
 ]
 
 _lib = None
@@ -87,7 +88,15 @@ def lib() -> ctypes.CDLL:
         b.restype = c_int
         n_out = 4 if sfx == "bf16" else 3
         b.argtypes = [c_void_p] * 6 + dims + [c_void_p] * n_out + [c_void_p]
-    if L.msda_abi_version() != 1:
+    for sfx in ("f32", "bf16"):
+        f = getattr(L, f"msda_fused_forward_{sfx}")
+        f.restype = c_int
+        f.argtypes = [c_void_p] * 6 + [c_int] + dims + [c_void_p] * 3 + [c_void_p]
+        b = getattr(L, f"msda_fused_backward_{sfx}")
+        b.restype = c_int
+        n_out = 5 if sfx == "bf16" else 4
+        b.argtypes = [c_void_p] * 7 + [c_int] + dims + [c_void_p] * n_out + [c_void_p]
+    if L.msda_abi_version() != 2:
         raise RuntimeError("libmsda_sm100.so ABI version mismatch")
     _lib = L
     return L

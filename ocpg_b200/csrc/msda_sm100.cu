@@ -309,6 +309,73 @@ struct TaskWalk {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Fused module path: the elementwise work MSDeformAttn.forward does around the
+// operator -- softmax of the attention logits over the L*P points (ms_deform_attn.py:101-102) and
+// sampling_locations = reference_points + offsets / (W_l, H_l) (2-d references, :104-107) or
+// reference_xy + offsets / P * reference_wh * 0.5 (4-d boxes, :108-110) -- folded into the staging phase of
+// the kernels, and its backward (softmax gradient, offset scaling) into the backward's last stage.  In this
+// mode `loc` holds the raw offsets and `attn` the raw logits.  The arithmetic keeps torch's operation order
+// (true divisions, no contraction) so the locations are bit-identical to the unfused module's.
+// ------------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const float *ref;        // [N][Lq][L][ref_dim] reference points
+    int ref_dim;             // 2 or 4
+    float *loc_out;          // forward, optional: sampling_locations [N][Lq][M][L][P][2]
+    float *attn_out;         // forward, optional: attention_weights  [N][Lq][M][L][P]
+    float *grad_loc_out;     // backward, optional: d/d sampling_locations (the caller sums it into grad_reference_points)
+};
+
+__device__ __forceinline__ float group_max(float v) {      // over the 8 lanes of a group
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ float group_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v + __shfl_xor_sync(0xffffffffu, v, 4);
+}
+
+// In: xy[r] = raw offsets, a[r] = raw logits of this lane's points (8*r + cl) of query `nq`.  Out: xy[r] = sampling
+// locations, a[r] = softmax probabilities (0 for lanes without a point).  Must be called by all 32 lanes.
+template <int ROUNDS>
+__device__ __forceinline__ void fused_softmax_and_locations(float2 (&xy)[ROUNDS], float (&a)[ROUNDS], bool query_on, int cl,
+                                                            int pts, uint32_t lv, const LevelTable &lt, const Dims &d,
+                                                            const FusedArgs &fa, int64_t nq, int64_t row) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r)
+        if (query_on && 8 * r + cl < pts) mx = fmaxf(mx, a[r]);
+    mx = group_max(mx);
+    float e[ROUNDS], sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        e[r] = (query_on && 8 * r + cl < pts) ? expf(a[r] - mx) : 0.f;
+        sum += e[r];
+    }
+    sum = group_sum(sum);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const bool on = query_on && 8 * r + cl < pts;
+        a[r] = on ? __fdiv_rn(e[r], sum) : 0.f;
+        if (!on) continue;
+        const int l = (lv >> (8 * r)) & 0xff;
+        if (fa.ref_dim == 2) {
+            const float2 rp = __ldg(reinterpret_cast<const float2 *>(fa.ref) + (nq * d.L + l));
+            xy[r].x = __fadd_rn(rp.x, __fdiv_rn(xy[r].x, (float)lt.W[l]));
+            xy[r].y = __fadd_rn(rp.y, __fdiv_rn(xy[r].y, (float)lt.H[l]));
+        } else {
+            const float4 rp = __ldg(reinterpret_cast<const float4 *>(fa.ref) + (nq * d.L + l));
+            const float fp = (float)d.P;
+            xy[r].x = __fadd_rn(rp.x, __fmul_rn(__fmul_rn(__fdiv_rn(xy[r].x, fp), rp.z), 0.5f));
+            xy[r].y = __fadd_rn(rp.y, __fmul_rn(__fmul_rn(__fdiv_rn(xy[r].y, fp), rp.w), 0.5f));
+        }
+        if (fa.loc_out) *reinterpret_cast<float2 *>(fa.loc_out + (row * pts + 8 * r + cl) * 2) = xy[r];
+        if (fa.attn_out) fa.attn_out[row * pts + 8 * r + cl] = a[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tiled forward, D = 32.  ROUNDS = ceil(L*P / 8): lane `cl` of a group stages points cl, 8+cl, ... of the
 // group's query (slots past L*P carry zero weights), then every lane gathers all of them branch-free.
 //   per point and warp: 2 broadcast LDS.128 (weights, offsets) + 4 LDG.128 (four rows each) + 8 FFMA2.
@@ -321,10 +388,10 @@ template <int ROUNDS, int WARPS> struct FwdSmem {
 };
 extern __shared__ __align__(16) unsigned char msda_smem[];
 
-template <typename VT, int ROUNDS, int WARPS>
+template <typename VT, int ROUNDS, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
 msda_fwd_tiled(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ start,
-               const float *__restrict__ loc, const float *__restrict__ attn, VT *__restrict__ out, Dims d) {
+               const float *__restrict__ loc, const float *__restrict__ attn, VT *__restrict__ out, Dims d, FusedArgs fa) {
     using IO = RowIO<VT>;
     using Vec = typename IO::Vec;
     constexpr int kTaskQueries = Tile<WARPS>::kQueries;
@@ -362,6 +429,8 @@ msda_fwd_tiled(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 a[r] = ld_stream_f1(attn + row * pts + 8 * r + cl);
             }
         }
+        if constexpr (FUSED)
+            fused_softmax_and_locations<ROUNDS>(xy, a, q >= 0, cl, pts, lv, lt, d, fa, (int64_t)t.n * d.Lq + max(q, 0), row);
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int l = (lv >> (8 * r)) & 0xff;
@@ -416,11 +485,12 @@ template <int WARPS> struct BwdSmem {
     float4 own[WARPS][32][2];   // per lane: its own point's bilinear weights; lx, ly, attention, corner validity
 };
 
-template <typename VT, int ROUNDS, int WARPS>
+template <typename VT, int ROUNDS, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
 msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ start, const float *__restrict__ loc, const float *__restrict__ attn,
-               float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d) {
+               float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d,
+               FusedArgs fa) {
     using IO = RowIO<VT>;
     using Vec = typename IO::Vec;
     constexpr int kTaskQueries = Tile<WARPS>::kQueries;
@@ -469,6 +539,15 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
                 a[r] = ld_stream_f1(attn + row * pts + 8 * r + cl);
             }
         }
+        const int64_t nq = (int64_t)t.n * d.Lq + max(q, 0);
+        if constexpr (FUSED) {
+            FusedArgs fwd_only = fa;       // the backward re-derives probabilities and locations; it emits neither
+            fwd_only.loc_out = nullptr; fwd_only.attn_out = nullptr;
+            fused_softmax_and_locations<ROUNDS>(xy, a, q >= 0, cl, pts, lv, lt, d, fwd_only, nq, row);
+        }
+        float g_prob[ROUNDS];      // fused mode: d/d probability of this lane's points, kept for the softmax gradient
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) g_prob[r] = 0.f;
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int pt = 8 * r + cl;
@@ -532,10 +611,37 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
                 const float ga = ow.x * q00 + ow.y * q01 + ow.z * q10 + ow.w * q11;                   // :156
                 const float gx = hy * (q01 - q00) + ly * (q11 - q10);                                 // :157
                 const float gy = hx * (q10 - q00) + lx * (q11 - q01);                                 // :158
-                grad_attn[row * pts + pt] = ga;
-                *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) =
-                    make_float2((float)lt.W[l] * a_own * gx, (float)lt.H[l] * a_own * gy);
+                const float2 gl = make_float2((float)lt.W[l] * a_own * gx, (float)lt.H[l] * a_own * gy);
+                if constexpr (!FUSED) {
+                    grad_attn[row * pts + pt] = ga;
+                    *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) = gl;
+                } else {
+                    // d/d offsets through sampling_locations = ref + offsets / (W, H)            (ms_deform_attn.py:104-107)
+                    //                          or           = ref_xy + offsets / P * ref_wh * 0.5   (:108-110)
+                    g_prob[r] = ga;
+                    if (fa.grad_loc_out) *reinterpret_cast<float2 *>(fa.grad_loc_out + (row * pts + pt) * 2) = gl;
+                    float2 go_;
+                    if (fa.ref_dim == 2) {
+                        go_ = make_float2(__fdiv_rn(gl.x, (float)lt.W[l]), __fdiv_rn(gl.y, (float)lt.H[l]));
+                    } else {
+                        const float4 rp = __ldg(reinterpret_cast<const float4 *>(fa.ref) + (nq * d.L + l));
+                        const float fp = (float)d.P;
+                        go_ = make_float2(__fdiv_rn(__fmul_rn(__fmul_rn(gl.x, 0.5f), rp.z), fp),
+                                          __fdiv_rn(__fmul_rn(__fmul_rn(gl.y, 0.5f), rp.w), fp));
+                    }
+                    *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) = go_;
+                }
             }
+        }
+        if constexpr (FUSED) {
+            // softmax gradient: d logit_i = p_i * (g_i - sum_j p_j g_j) over the L*P points of this (query, head)
+            float dot = 0.f;
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) dot = fmaf(a[r], g_prob[r], dot);
+            dot = group_sum(dot);
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r)
+                if (q >= 0 && 8 * r + cl < pts) grad_attn[row * pts + 8 * r + cl] = a[r] * (g_prob[r] - dot);
         }
         __syncwarp();
     }
@@ -731,63 +837,75 @@ int configure(K kernel, size_t smem) {
     return MSDA_OK;
 }
 
+// `fa == nullptr`: the plain operator; otherwise the fused module path (FusedArgs).
 template <typename VT, int ROUNDS, int WARPS>
 int launch_fwd_one(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
-                   VT *out, const Dims &d, cudaStream_t st) {
+                   VT *out, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
     const size_t smem = sizeof(FwdSmem<ROUNDS, WARPS>);
-    if (const int rc = configure(msda_fwd_tiled<VT, ROUNDS, WARPS>, smem)) return rc;
     const int grid = grid_for(32 / WARPS, g_fwd_ctas_per_sm);
-    msda_fwd_tiled<VT, ROUNDS, WARPS><<<grid, WARPS * 32, smem, st>>>(value, shapes, start, loc, attn, out, d);
+    if (fa) {
+        if (const int rc = configure(msda_fwd_tiled<VT, ROUNDS, WARPS, true>, smem)) return rc;
+        msda_fwd_tiled<VT, ROUNDS, WARPS, true><<<grid, WARPS * 32, smem, st>>>(value, shapes, start, loc, attn, out, d, *fa);
+    } else {
+        if (const int rc = configure(msda_fwd_tiled<VT, ROUNDS, WARPS, false>, smem)) return rc;
+        msda_fwd_tiled<VT, ROUNDS, WARPS, false><<<grid, WARPS * 32, smem, st>>>(value, shapes, start, loc, attn, out, d, FusedArgs{});
+    }
     return after_launch("msda_fwd_tiled");
 }
 
 template <typename VT, int ROUNDS>
 int launch_fwd_rounds(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
-                      VT *out, const Dims &d, cudaStream_t st) {
+                      VT *out, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
     switch (warps_for(g_fwd_warps, kDefaultFwdWarps)) {
-        case 8: return launch_fwd_one<VT, ROUNDS, 8>(value, shapes, start, loc, attn, out, d, st);
-        default: return launch_fwd_one<VT, ROUNDS, 16>(value, shapes, start, loc, attn, out, d, st);
+        case 8: return launch_fwd_one<VT, ROUNDS, 8>(value, shapes, start, loc, attn, out, d, fa, st);
+        default: return launch_fwd_one<VT, ROUNDS, 16>(value, shapes, start, loc, attn, out, d, fa, st);
     }
 }
 
 template <typename VT>
 int launch_fwd_tiled(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
-                     VT *out, const Dims &d, cudaStream_t st) {
+                     VT *out, const Dims &d, cudaStream_t st, const FusedArgs *fa = nullptr) {
     switch ((d.L * d.P + 7) / 8) {
-        case 1: return launch_fwd_rounds<VT, 1>(value, shapes, start, loc, attn, out, d, st);
-        case 2: return launch_fwd_rounds<VT, 2>(value, shapes, start, loc, attn, out, d, st);
-        case 3: return launch_fwd_rounds<VT, 3>(value, shapes, start, loc, attn, out, d, st);
-        default: return launch_fwd_rounds<VT, 4>(value, shapes, start, loc, attn, out, d, st);
+        case 1: return launch_fwd_rounds<VT, 1>(value, shapes, start, loc, attn, out, d, fa, st);
+        case 2: return launch_fwd_rounds<VT, 2>(value, shapes, start, loc, attn, out, d, fa, st);
+        case 3: return launch_fwd_rounds<VT, 3>(value, shapes, start, loc, attn, out, d, fa, st);
+        default: return launch_fwd_rounds<VT, 4>(value, shapes, start, loc, attn, out, d, fa, st);
     }
 }
 
 template <typename VT, int ROUNDS, int WARPS>
 int launch_bwd_one(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
-                   const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st) {
+                   const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
     const size_t smem = sizeof(BwdSmem<WARPS>);
-    if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS>, smem)) return rc;
     const int grid = grid_for(32 / WARPS, g_bwd_ctas_per_sm);
-    msda_bwd_tiled<VT, ROUNDS, WARPS><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d);
+    if (fa) {
+        if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS, true>, smem)) return rc;
+        msda_bwd_tiled<VT, ROUNDS, WARPS, true><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, *fa);
+    } else {
+        if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS, false>, smem)) return rc;
+        msda_bwd_tiled<VT, ROUNDS, WARPS, false><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, FusedArgs{});
+    }
     return after_launch("msda_bwd_tiled");
 }
 
 template <typename VT, int ROUNDS>
 int launch_bwd_rounds(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
-                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st) {
+                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
     switch (warps_for(g_bwd_warps, kDefaultBwdWarps)) {
-        case 8: return launch_bwd_one<VT, ROUNDS, 8>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
-        default: return launch_bwd_one<VT, ROUNDS, 16>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+        case 8: return launch_bwd_one<VT, ROUNDS, 8>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
+        default: return launch_bwd_one<VT, ROUNDS, 16>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
     }
 }
 
 template <typename VT>
 int launch_bwd_tiled(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
-                     const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st) {
+                     const float *attn, float *gv, float *gl, float *ga, const Dims &d, cudaStream_t st,
+                     const FusedArgs *fa = nullptr) {
     switch ((d.L * d.P + 7) / 8) {
-        case 1: return launch_bwd_rounds<VT, 1>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
-        case 2: return launch_bwd_rounds<VT, 2>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
-        case 3: return launch_bwd_rounds<VT, 3>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
-        default: return launch_bwd_rounds<VT, 4>(go, value, shapes, start, loc, attn, gv, gl, ga, d, st);
+        case 1: return launch_bwd_rounds<VT, 1>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
+        case 2: return launch_bwd_rounds<VT, 2>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
+        case 3: return launch_bwd_rounds<VT, 3>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
+        default: return launch_bwd_rounds<VT, 4>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
     }
 }
 
@@ -947,6 +1065,96 @@ int msda_backward_bf16(const uint16_t *go, const uint16_t *value, const int64_t 
     if (gv16 && nval > 0) {
         if (misaligned(gv16, 8)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: misaligned grad_value_bf16");
         const int64_t n4 = nval / 4;   // D == 32, so nval is a multiple of 4
+        const int grid = (int)((n4 + 255) / 256 < (int64_t)sm_count() * 16 ? (n4 + 255) / 256 : (int64_t)sm_count() * 16);
+        msda_f32_to_bf16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(gv32), reinterpret_cast<uint2 *>(gv16), n4);
+        return after_launch("msda_f32_to_bf16");
+    }
+    return MSDA_OK;
+}
+
+}  // extern "C"
+
+// ---- fused module path: offsets / logits / reference points in, softmax + location arithmetic inside the kernels ----
+namespace {
+template <typename VT>
+int fused_forward_any(const char *what, const VT *value, const int64_t *shapes, const int64_t *start, const float *offsets,
+                      const float *logits, const float *ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P,
+                      VT *out, float *loc_out, float *attn_out, msda_stream_t stream) {
+    if (const int rc = check_dims(N, S, M, D, L, Lq, P)) return rc;
+    if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_forward: ref_dim must be 2 or 4");
+    if (!tiled_ok(D, L, P)) return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_forward: only channels == 32, num_levels <= 16, num_levels*num_point <= 32 (use the unfused operator)");
+    if ((int64_t)N * Lq == 0) return MSDA_OK;
+    if (!value || !shapes || !start || !offsets || !logits || !ref || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, what);
+    if (misaligned(value, 4 * sizeof(VT)) || misaligned(out, 4 * sizeof(VT)) || misaligned(offsets, 8) ||
+        misaligned(ref, ref_dim == 2 ? 8 : 16) || (loc_out && misaligned(loc_out, 8)))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_forward: misaligned pointer");
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, (int)sizeof(VT));
+    const FusedArgs fa{ref, ref_dim, loc_out, attn_out, nullptr};
+    return launch_fwd_tiled<VT>(value, shapes, start, offsets, logits, out, d, (cudaStream_t)stream, &fa);
+}
+
+template <typename VT>
+int fused_backward_any(const char *what, const VT *go, const VT *value, const int64_t *shapes, const int64_t *start,
+                       const float *offsets, const float *logits, const float *ref, int ref_dim, int N, int S, int M, int D,
+                       int L, int Lq, int P, float *gv32, float *g_off, float *g_logits, float *g_loc, cudaStream_t st) {
+    if (const int rc = check_dims(N, S, M, D, L, Lq, P)) return rc;
+    if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward: ref_dim must be 2 or 4");
+    if (!tiled_ok(D, L, P)) return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward: only channels == 32, num_levels <= 16, num_levels*num_point <= 32 (use the unfused operator)");
+    if (!gv32 && N > 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward: null grad_value");
+    if (N > 0) {
+        const cudaError_t e = cudaMemsetAsync(gv32, 0, sizeof(float) * (size_t)N * S * M * D, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_fused_backward: memset(grad_value)");
+    }
+    if ((int64_t)N * Lq == 0) return MSDA_OK;
+    if (!go || !value || !shapes || !start || !offsets || !logits || !ref || !g_off || !g_logits) return fail(MSDA_ERR_INVALID_ARGUMENT, what);
+    if (misaligned(value, 4 * sizeof(VT)) || misaligned(go, 4 * sizeof(VT)) || misaligned(gv32, 16) || misaligned(offsets, 8) ||
+        misaligned(g_off, 8) || misaligned(ref, ref_dim == 2 ? 8 : 16) || (g_loc && misaligned(g_loc, 8)))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward: misaligned pointer");
+    const Dims d = make_dims(N, S, M, D, L, Lq, P, (int)sizeof(VT));
+    const FusedArgs fa{ref, ref_dim, nullptr, nullptr, g_loc};
+    return launch_bwd_tiled<VT>(go, value, shapes, start, offsets, logits, gv32, g_off, g_logits, d, st, &fa);
+}
+}  // namespace
+
+extern "C" {
+
+int msda_fused_forward_f32(const float *value, const int64_t *shapes, const int64_t *start, const float *offsets,
+                           const float *logits, const float *ref, int ref_dim, int N, int S, int M, int D, int L, int Lq,
+                           int P, float *out, float *loc_out, float *attn_out, msda_stream_t stream) {
+    return fused_forward_any<float>("msda_fused_forward_f32: null pointer", value, shapes, start, offsets, logits, ref, ref_dim,
+                                    N, S, M, D, L, Lq, P, out, loc_out, attn_out, stream);
+}
+
+int msda_fused_backward_f32(const float *go, const float *value, const int64_t *shapes, const int64_t *start,
+                            const float *offsets, const float *logits, const float *ref, int ref_dim, int N, int S, int M,
+                            int D, int L, int Lq, int P, float *gv, float *g_off, float *g_logits, float *g_loc,
+                            msda_stream_t stream) {
+    return fused_backward_any<float>("msda_fused_backward_f32: null pointer", go, value, shapes, start, offsets, logits, ref,
+                                     ref_dim, N, S, M, D, L, Lq, P, gv, g_off, g_logits, g_loc, (cudaStream_t)stream);
+}
+
+int msda_fused_forward_bf16(const uint16_t *value, const int64_t *shapes, const int64_t *start, const float *offsets,
+                            const float *logits, const float *ref, int ref_dim, int N, int S, int M, int D, int L, int Lq,
+                            int P, uint16_t *out, float *loc_out, float *attn_out, msda_stream_t stream) {
+    return fused_forward_any<__nv_bfloat16>("msda_fused_forward_bf16: null pointer", reinterpret_cast<const __nv_bfloat16 *>(value),
+                                            shapes, start, offsets, logits, ref, ref_dim, N, S, M, D, L, Lq, P,
+                                            reinterpret_cast<__nv_bfloat16 *>(out), loc_out, attn_out, stream);
+}
+
+int msda_fused_backward_bf16(const uint16_t *go, const uint16_t *value, const int64_t *shapes, const int64_t *start,
+                             const float *offsets, const float *logits, const float *ref, int ref_dim, int N, int S, int M,
+                             int D, int L, int Lq, int P, float *gv32, uint16_t *gv16, float *g_off, float *g_logits,
+                             float *g_loc, msda_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (const int rc = fused_backward_any<__nv_bfloat16>("msda_fused_backward_bf16: null pointer",
+                                                         reinterpret_cast<const __nv_bfloat16 *>(go),
+                                                         reinterpret_cast<const __nv_bfloat16 *>(value), shapes, start, offsets,
+                                                         logits, ref, ref_dim, N, S, M, D, L, Lq, P, gv32, g_off, g_logits, g_loc, st))
+        return rc;
+    const int64_t nval = (int64_t)N * S * M * D;
+    if (gv16 && nval > 0) {
+        if (misaligned(gv16, 8)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward_bf16: misaligned grad_value_bf16");
+        const int64_t n4 = nval / 4;
         const int grid = (int)((n4 + 255) / 256 < (int64_t)sm_count() * 16 ? (n4 + 255) / 256 : (int64_t)sm_count() * 16);
         msda_f32_to_bf16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(gv32), reinterpret_cast<uint2 *>(gv16), n4);
         return after_launch("msda_f32_to_bf16");

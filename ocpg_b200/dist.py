@@ -6,7 +6,7 @@ main.py:62).  torch.distributed is used only for the barrier and the max-over-ra
 from __future__ import annotations
 
 import os
-from typing import Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -59,6 +59,64 @@ def local_frames(n_frames_global: int) -> Tuple[int, int]:
     """This rank's contiguous block of the global frame axis: (first_frame, n_local)."""
     rank, _, world = env_world()
     return shard_frames(n_frames_global, world, rank)
+
+
+class BucketedGradAllReduce:
+    """All-reduce of the REPLICATED weights' gradients -- the only collective of the encoder benchmark
+    (BASELINE.json configs[4]; the op itself has none).  Parameters are grouped in buckets (one per encoder
+    layer); a bucket's all-reduce is issued from a post-accumulate-grad hook the moment its last gradient is
+    ready, so it runs on the communication stream while the backward of the earlier layers is still computing.
+    ``finish()`` waits for the buckets and writes the averaged gradients back.
+
+    With gradient accumulation over micro-batches set ``enabled = False`` for all but the last micro-batch.
+    Without an initialised process group it does nothing."""
+
+    def __init__(self, buckets: Sequence[Iterable[torch.nn.Parameter]], average: bool = True):
+        self.buckets: List[List[torch.nn.Parameter]] = [[p for p in b if p.requires_grad] for b in buckets]
+        self.average = average
+        self.enabled = True
+        self._pending = [len(b) for b in self.buckets]
+        self._inflight = []
+        self._handles = []
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _make_hook(self, bi: int):
+        def hook(_param):
+            if not self.enabled or not dist.is_initialized():
+                return
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                bucket = self.buckets[bi]
+                flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+                self._inflight.append((bi, flat, work))
+        return hook
+
+    def finish(self) -> int:
+        """Wait for every issued bucket, scatter the reduced values back into ``.grad``; returns the number of
+        gradient bytes this rank contributed to collectives."""
+        nbytes = 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        for bi, flat, work in self._inflight:
+            work.wait()
+            if self.average:
+                flat.div_(world)
+            off = 0
+            for p in self.buckets[bi]:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+            nbytes += flat.numel() * flat.element_size()
+        self._inflight.clear()
+        self._pending = [len(b) for b in self.buckets]
+        return nbytes
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles.clear()
 
 
 def finalize():

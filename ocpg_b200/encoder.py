@@ -1,0 +1,99 @@
+"""The caller of the hot path: OCPG's deformable-transformer encoder, re-hosted around ocpg_b200.MSDeformAttn.
+
+Reference: models/deformable_transformer.py -- ``DeformableTransformerEncoderLayer`` (:220-260) and
+``DeformableTransformerEncoder`` (:263-290).  Same constructor arguments, same sub-module names
+(``self_attn``, ``norm1``, ``linear1``, ``linear2``, ``norm2``, ``layers.N``) so a reference state_dict loads
+unchanged, same forward signatures and results.  This is the harness BASELINE.json configs[2] and [4] are
+measured on (6-layer encoder forward + backward); it is not a re-implementation of
+the rest of the model.
+
+Differences from the reference, all on the host side:
+  * ``fused=True`` (default) switches every layer's MSDeformAttn to the fused kernels and stops it from
+    materialising sampling_locations / attention_weights, which the encoder throws away (:251);
+  * the reference wraps the attention in ``autocast(enabled=False)`` (:250); so does this.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .modules import MSDeformAttn
+
+
+def _activation(name: str):
+    try:
+        return {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}[name]
+    except KeyError:
+        raise RuntimeError(f"activation should be relu/gelu, not {name}.")      # deformable_transformer.py:_get_activation_fn
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 fused=True):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.self_attn.fused = bool(fused)
+        self.self_attn.emit_sampling = not fused
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward_ffn(self, src):
+        hidden = self.dropout2(self.activation(self.linear1(src)))
+        return self.norm2(src + self.dropout3(self.linear2(hidden)))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        with torch.autocast(device_type=src.device.type, enabled=False):
+            attn_out = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
+                                      level_start_index, padding_mask)[0]
+        src = self.norm1(src + self.dropout1(attn_out))
+        return self.forward_ffn(src)
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        """(N, S, L, 2): pixel centres of every query's own level, divided by that level's valid extent and
+        re-scaled to every level's valid ratio (:268-281).  ``spatial_shapes`` is iterated on the host, as in
+        the reference (one small device->host copy per call)."""
+        per_level = []
+        shapes = spatial_shapes.tolist() if isinstance(spatial_shapes, torch.Tensor) else list(spatial_shapes)
+        for lvl, (h, w) in enumerate(shapes):
+            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
+            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            gy = gy.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * h)
+            gx = gx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * w)
+            per_level.append(torch.stack((gx, gy), -1))
+        points = torch.cat(per_level, 1)
+        return points[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+        reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        output = src
+        for layer in self.layers:
+            output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
+        return output
+
+
+def build_encoder(num_layers=6, d_model=256, d_ffn=2048, dropout=0.0, n_levels=4, n_heads=8, n_points=4, fused=True):
+    """The benchmark configuration: 6 layers (BASELINE.json), d_ffn=2048 (opts.py:54), dropout off for parity."""
+    layer = DeformableTransformerEncoderLayer(d_model, d_ffn, dropout, "relu", n_levels, n_heads, n_points, fused=fused)
+    return DeformableTransformerEncoder(layer, num_layers)

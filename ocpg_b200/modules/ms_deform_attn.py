@@ -7,6 +7,12 @@ same ``forward`` signature and the same **3-tuple** return
 ``(output, sampling_locations, attention_weights)`` (:118 -- OCPG's decoder consumes the last two,
 deformable_transformer.py:365-375).
 
+Opt-in extension: ``module.fused = True`` runs the softmax and the
+sampling-location arithmetic (:101-110) inside the kernels (MSDeformAttnFusedFunction) -- same parameters, same
+result; ``module.emit_sampling = False`` additionally skips materialising ``sampling_locations`` /
+``attention_weights`` (returned as ``None``), which is what the encoder layers want
+(deformable_transformer.py:251 discards them).  The default (``fused = False``) is the reference's exact graph.
+
 Host-side differences:
   * the sampling op is ocpg_b200's sm_100a kernels (through MSDeformAttnFunction);
   * the ``sum(H*W) == Len_in`` check (:94), which costs the reference one device->host sync per call, is
@@ -21,7 +27,9 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import MultiScaleDeformableAttention as MSDA
 from ..functions import MSDeformAttnFunction
+from ..functions.ms_deform_attn_func import MSDeformAttnFusedFunction
 
 
 def _is_power_of_2(n):
@@ -53,6 +61,8 @@ class MSDeformAttn(nn.Module):
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
         self._shape_ok = {}            # (data_ptr, version, Len_in) of spatial_shapes tensors already verified
+        self.fused = False             # True: softmax + sampling locations inside the kernels
+        self.emit_sampling = True      # fused only: materialise sampling_locations / attention_weights for the caller
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -105,6 +115,15 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask[..., None], float(0))           # :97-98
         value = value.view(N, Len_in, M, self.d_model // M)
         offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)                # :100
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
+                reference_points.shape[-1]))
+        if self.fused and value.is_cuda and MSDA.fused_supported(value, L, P):
+            logits = self.attention_weights(query).view(N, Len_q, M, L * P)
+            output, sampling_locations, weights = MSDeformAttnFusedFunction.apply(
+                value.contiguous(), input_spatial_shapes, input_level_start_index, offsets.contiguous(),
+                logits.contiguous(), reference_points.to(torch.float32).contiguous(), self.im2col_step, self.emit_sampling)
+            return self.output_proj(output), sampling_locations, weights
         weights = F.softmax(self.attention_weights(query).view(N, Len_q, M, L * P), -1)  # :101-102
         weights = weights.view(N, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:                                              # :104-107

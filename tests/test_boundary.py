@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
         assert hasattr(L, s), s
-    assert ocpg_b200.lib().msda_abi_version() == 1
+    assert ocpg_b200.lib().msda_abi_version() == 2
 
 
 def test_library_is_sm100a_only():
@@ -146,3 +146,20 @@ def test_workload_shapes_and_bytes():
         f, n = shard_frames(10, 3, r)
         covered += list(range(f, f + n))
     assert covered == list(range(10))
+
+
+def test_encoder_mirrors_reference_layout():
+    """The encoder harness keeps the reference's sub-module names (deformable_transformer.py:220-290) so its
+    state_dict keys are the reference's; 6 layers x (MSDeformAttn + 2 LayerNorm + FFN) = 7 693 056 weights
+    (SURVEY.md section 8e)."""
+    from ocpg_b200.encoder import DeformableTransformerEncoder, build_encoder
+    enc = build_encoder(num_layers=6, d_ffn=2048)
+    keys = set(enc.state_dict())
+    for k in ("layers.0.self_attn.sampling_offsets.weight", "layers.5.self_attn.output_proj.bias", "layers.2.norm1.weight",
+              "layers.3.linear1.weight", "layers.4.linear2.bias", "layers.1.norm2.bias"):
+        assert k in keys, k
+    assert sum(p.numel() for p in enc.parameters()) == 7693056
+    shapes = torch.tensor([(3, 4), (2, 2)])
+    ref = DeformableTransformerEncoder.get_reference_points(shapes, torch.ones(2, 2, 2), "cpu")
+    assert ref.shape == (2, 16, 2, 2)
+    assert torch.allclose(ref[0, 0, 0], torch.tensor([0.5 / 4, 0.5 / 3])) and torch.allclose(ref[0, 12, 1], torch.tensor([0.25, 0.25]))

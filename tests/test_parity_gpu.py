@@ -349,12 +349,14 @@ class _OracleModule(torch.nn.Module):
         return m.output_proj(msda_grid_sample(value, shapes, loc, aw)), loc, aw
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("ref_dim,use_mask", [(2, False), (2, True), (4, False)])
-def test_module_end_to_end(dev, ref_dim, use_mask):
+def test_module_end_to_end(dev, ref_dim, use_mask, fused):
     from ocpg_b200 import MSDeformAttn
     from oracle.compare import rel_err
     torch.manual_seed(0)
     mod = MSDeformAttn(256, 4, 8, 4).to(dev)
+    mod.fused = fused
     with torch.no_grad():                                  # make offsets / logits depend on the query
         mod.sampling_offsets.weight.normal_(0, 0.02)
         mod.attention_weights.weight.normal_(0, 0.05)
@@ -369,19 +371,114 @@ def test_module_end_to_end(dev, ref_dim, use_mask):
     if ref_dim == 4:
         refp[..., 2:] = refp[..., 2:] * 0.3 + 0.05
     mask = (torch.rand(N, S, device=dev) < 0.1) if use_mask else None
-    src.requires_grad_(True); query.requires_grad_(True)
+    src.requires_grad_(True); query.requires_grad_(True); refp.requires_grad_(True)
     out, loc, aw = mod(query, refp, src, shapes, start, mask)
     assert loc.shape == (N, Lq, 8, 4, 4, 2) and aw.shape == (N, Lq, 8, 4, 4)      # 3-tuple, reference :118
     g = torch.randn_like(out)
     out.backward(g)
     src64, q64 = src.detach().double().requires_grad_(True), query.detach().double().requires_grad_(True)
-    rout, rloc, raw = ref(q64, refp.double(), src64, shapes, start, mask)
+    refp64 = refp.detach().double().requires_grad_(True)
+    rout, rloc, raw = ref(q64, refp64, src64, shapes, start, mask)
     rout.backward(g.double())
+    assert rel_err(refp.grad, refp64.grad) <= 2e-3
     # loc / aw come out of fp32 nn.Linear + softmax (cuBLAS fp32, not our kernels): a few fp32 ulps vs the fp64 module
     assert rel_err(out, rout) <= 5e-5 and rel_err(loc, rloc) <= 5e-6 and rel_err(aw, raw) <= 5e-6
     assert rel_err(src.grad, src64.grad) <= 2e-4 and rel_err(query.grad, q64.grad) <= 2e-3
     for (n1, p1), (n2, p2) in zip(mod.named_parameters(), ref.m.named_parameters()):
         assert n1 == n2 and rel_err(p1.grad, p2.grad) <= 2e-3, n1
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("regime", ["init", "uniform"])
+def test_fused_operator_matches_unfused(dev, ref_dim, regime):
+    """MSDeformAttnFusedFunction == softmax + location arithmetic in torch followed by MSDeformAttnFunction:
+    locations bit-identical (same operation order), everything else within a few fp32 ulps."""
+    from ocpg_b200 import MSDeformAttnFunction, MSDeformAttnFusedFunction
+    from ocpg_b200.workloads import encoder_reference_points, encoder_workload
+    from oracle.compare import rel_err
+    wl = encoder_workload("t", 3, 96, 160)
+    g = torch.Generator(device=dev).manual_seed(5)
+    N, S, M, D, L, P, Lq = wl.n_frames, wl.S, 8, 32, wl.L, 4, wl.S
+    kw = dict(device=dev, generator=g)
+    shapes = torch.tensor(wl.levels, device=dev)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, S, M, D, **kw)
+    offsets = torch.randn(N, Lq, M, L, P, 2, **kw) * (2.0 if regime == "init" else 40.0)
+    logits = torch.randn(N, Lq, M, L * P, **kw) * 2
+    ref2 = encoder_reference_points(wl.levels, dev)[None].expand(N, -1, -1, -1).contiguous()
+    refp = ref2 if ref_dim == 2 else torch.cat((ref2, torch.rand(N, Lq, L, 2, **kw) * 0.3 + 0.05), -1)
+    gout = torch.randn(N, Lq, M * D, **kw)
+
+    def leaves():
+        return [t.clone().requires_grad_(True) for t in (value, offsets, logits, refp)]
+
+    v1, o1, l1, r1 = leaves()
+    out1, loc1, aw1 = MSDeformAttnFusedFunction.apply(v1, shapes, start, o1, l1, r1, 64, True)
+    out1.backward(gout)
+    v2, o2, l2, r2 = leaves()
+    aw2 = torch.softmax(l2, -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        wh = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc2 = r2[:, :, None, :, None, :] + o2 / wh[None, None, None, :, None, :]
+    else:
+        loc2 = r2[:, :, None, :, None, :2] + o2 / P * r2[:, :, None, :, None, 2:] * 0.5
+    out2 = MSDeformAttnFunction.apply(v2, shapes, start, loc2.contiguous(), aw2.contiguous(), 64)
+    out2.backward(gout)
+    assert not loc1.requires_grad and not aw1.requires_grad
+    assert torch.equal(loc1, loc2.detach()), (loc1 - loc2).abs().max()
+    assert rel_err(aw1, aw2) <= 1e-6 and rel_err(out1, out2) <= 2e-6
+    assert rel_err(v1.grad, v2.grad) <= 1e-5
+    assert rel_err(o1.grad, o2.grad) <= 1e-5 and rel_err(l1.grad, l2.grad) <= 2e-5
+    assert rel_err(r1.grad, r2.grad) <= 2e-5
+    # emit=False returns no locations and the same output
+    out3, loc3, aw3 = MSDeformAttnFusedFunction.apply(value, shapes, start, offsets, logits, refp, 64, False)
+    assert loc3 is None and aw3 is None and torch.equal(out3, out1.detach())
+
+
+def test_fused_rejects_unsupported_layouts(dev):
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    v = torch.randn(1, 6, 2, 16, device=dev)                     # 16 channels per head: generic kernels only
+    shapes = torch.tensor([(2, 3)], device=dev); start = torch.zeros(1, dtype=torch.int64, device=dev)
+    assert not MSDA.fused_supported(v, 1, 2)
+    with pytest.raises(RuntimeError, match="unfused"):
+        MSDA.ms_deform_attn_fused_forward(v, shapes, start, torch.zeros(1, 3, 2, 1, 2, 2, device=dev),
+                                          torch.zeros(1, 3, 2, 2, device=dev), torch.rand(1, 3, 1, 2, device=dev), 64)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_encoder_layers_vs_fp64_oracle(dev, fused):
+    """The caller of the hot path (deformable_transformer.py:220-290): a 2-layer encoder forward + backward on the
+    GPU vs the same weights in fp64 with the op replaced by the grid_sample port, incl. valid_ratios < 1, positional
+    embeddings and a padding mask."""
+    from ocpg_b200.encoder import DeformableTransformerEncoder, build_encoder
+    from oracle.compare import rel_err
+    torch.manual_seed(1)
+    enc = build_encoder(num_layers=2, d_ffn=512, fused=fused).to(dev)
+    with torch.no_grad():
+        for layer in enc.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.02)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    ref = copy.deepcopy(enc).double()
+    for layer in ref.layers:                                   # fp64 oracle: reference graph, grid_sample op
+        layer.self_attn = _OracleModule(layer.self_attn)
+    shapes = torch.tensor([(12, 20), (6, 10), (3, 5), (2, 3)], device=dev)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S, N = int(shapes.prod(1).sum()), 3
+    src = torch.randn(N, S, 256, device=dev, requires_grad=True)
+    pos = torch.randn(N, S, 256, device=dev) * 0.1
+    vr = 0.8 + 0.2 * torch.rand(N, 4, 2, device=dev)
+    mask = torch.rand(N, S, device=dev) < 0.05
+    out = enc(src, shapes, start, vr, pos, mask)
+    g = torch.randn_like(out)
+    out.backward(g)
+    src64 = src.detach().double().requires_grad_(True)
+    rout = ref(src64, shapes, start, vr.double(), pos.double(), mask)
+    rout.backward(g.double())
+    assert rel_err(out, rout) <= 1e-4, rel_err(out, rout)
+    assert rel_err(src.grad, src64.grad) <= 1e-3
+    for (n1, p1), (n2, p2) in zip(enc.named_parameters(), ref.named_parameters()):
+        assert n1.replace("self_attn.", "") == n2.replace("self_attn.m.", ""), (n1, n2)
+        assert rel_err(p1.grad, p2.grad) <= 3e-3, (n1, rel_err(p1.grad, p2.grad))
 
 
 def test_autograd_function_grads_and_none_slots(dev):
