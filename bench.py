@@ -2,7 +2,7 @@
 """bench.py -- MSDeformAttn forward+backward throughput on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload a2d|ytvos|decoder] [--regime init|uniform] [--dtype f32|bf16]
+                    [--workload a2d|ytvos|decoder|encoder-a2d|encoder-ytvos] [--regime init|uniform] [--dtype f32|bf16]
 
 A *step* is one pass of the hot path -- MSDeformAttnFunction forward + backward (grad_value,
 grad_sampling_loc, grad_attn_weight) -- over one batch of synthetic input.  At N=1 the batch is
@@ -19,7 +19,8 @@ One JSON line is printed by rank 0:
                 device -> host copies of output and the three gradients, every step, all inside the timed
                 region (steps pipelined over three streams; wall clock around a synchronised region).
   roofline      for the dominant kernel (the backward): algorithmic bytes per launch / its mean launch
-                duration (CUDA events around each launch) vs the measured HBM peak (MEASURED_PEAKS.json).
+                duration (CUDA events around back-to-back graph replays of that kernel alone) vs the measured HBM
+                peak (MEASURED_PEAKS.json).
   cpu_baseline  the reference's CPU path (grid_sample formulation, oracle/grid_sample_port.py) timed on
                 this box's host cores, rank 0, N=1 only.
 `--impl reference` times only that CPU path (all host threads), same metric / config.
@@ -49,7 +50,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="a2d", choices=["a2d", "ytvos", "decoder"])
+    ap.add_argument("--workload", default="a2d", choices=["a2d", "ytvos", "decoder", "encoder-a2d", "encoder-ytvos"],
+                    help="a2d (default) = BASELINE.json configs[1]; encoder-* = the 6-layer encoder fwd+bwd with the NCCL "
+                         "all-reduce of weight gradients (configs[2], [4]; tools/bench_encoder.py, its own metric)")
+    ap.add_argument("--frames-per-gpu", type=int, default=0, help="encoder-* only")
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32", "bf16"], help="encoder-* only: GEMM precision policy")
     ap.add_argument("--regime", default="init", choices=["init", "uniform"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--input-sets", type=int, default=6)
@@ -202,6 +207,7 @@ def run_ours(args):
     rank, local_rank, world = D.init("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    local_cpus = D.bind_to_gpu_cpus(local_rank) if world > 1 else None    # NUMA-local pinned buffers for the e2e leg
     ocpg_b200.lib()                                                   # fail loudly if the extension is missing
     wl = pick_workload(args.workload)
     vdt = torch.bfloat16 if args.dtype == "bf16" else None
@@ -260,19 +266,46 @@ def run_ours(args):
     ms_per_step = ms_total / K
     value_qps = wl.queries * world / (ms_per_step * 1e-3)
 
-    # ---- per-kernel durations (events around each launch, same rotating inputs)
+    # ---- per-kernel durations: the same rotating inputs, one CUDA graph per (kernel, input set) so that no host
+    # launch latency sits between the events and the kernel; mean over `iters` back-to-back replays between one
+    # event pair, min over single replays.
     def time_kernel(fn, iters):
-        evs = []
-        torch.cuda._sleep(int(3e7))        # ~15 ms of GPU spin: every launch below is queued before the GPU gets to
-                                           # it, so the event pairs bracket pure device time (no host launch gaps)
-        for i in range(iters):
-            x = sets[i % R]
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(x); b.record()
-            evs.append((a, b))
+        if args.no_graph:
+            evs = []
+            torch.cuda._sleep(int(3e7))    # ~15 ms of GPU spin: the launches below are queued before the GPU gets to them
+            for i in range(iters):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(sets[i % R]); b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            ts = [a.elapsed_time(b) for a, b in evs]
+            return statistics.mean(ts), min(ts)
+        gs, keep_ = [], []
+        with torch.cuda.stream(torch.cuda.Stream()):
+            fn(sets[0])
         torch.cuda.synchronize()
-        ts = [a.elapsed_time(b) for a, b in evs]
-        return statistics.mean(ts), min(ts)
+        for x in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keep_.append(fn(x))
+            gs.append(g)
+        for i in range(R):
+            gs[i].replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            gs[i % R].replay()
+        b.record()
+        torch.cuda.synchronize()
+        mean = a.elapsed_time(b) / iters
+        singles = []
+        for i in range(min(iters, 12)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); gs[i % R].replay(); b.record()
+            torch.cuda.synchronize()
+            singles.append(a.elapsed_time(b))
+        return mean, min(singles)
 
     iters = min(K, 60)
     fwd_ms, fwd_min = time_kernel(lambda x: MSDA.ms_deform_attn_forward(
@@ -347,7 +380,8 @@ def run_ours(args):
         assert torch.equal(hout[(Ke - 1) % NB][0], ref_out.cpu()), "e2e pipeline returned a different output"
         e2e = {"value": wl.queries * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": Ke,
-               "pipeline": "3 streams (H2D | fwd+bwd | D2H), 2 buffer sets, pinned host memory"}
+               "pipeline": "3 streams (H2D | fwd+bwd | D2H), 2 buffer sets, pinned host memory",
+               "cpu_affinity": (f"{len(local_cpus)} cores local to the GPU (NVML)" if local_cpus else "unchanged")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -382,6 +416,14 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    if args.workload.startswith("encoder-"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_encoder
+        argv = ["--shape", args.workload.split("-", 1)[1], "--steps", str(args.steps if args.steps != 200 else 10),
+                "--warmup", str(min(args.warmup, 5)), "--gemm", args.gemm]
+        if args.frames_per_gpu:
+            argv += ["--frames-per-gpu", str(args.frames_per_gpu), "--micro", "16"]
+        return bench_encoder.main(argv)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

@@ -33,6 +33,29 @@ def init(backend: str = "nccl"):
     return rank, local_rank, world
 
 
+def bind_to_gpu_cpus(local_rank: int):
+    """Pin this process to the CPU cores NVML reports as local to its GPU, so that pinned host buffers are
+    first-touched on the GPU's own NUMA node and every rank's host<->device copies use its own socket's memory
+    (the e2e path of bench.py is PCIe-bound; without this all ranks share one socket's memory bandwidth).
+    Returns the CPU list, or None if NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def barrier():
     if dist.is_initialized():
         dist.barrier()
