@@ -162,6 +162,8 @@ uint64_t msda_launch_count(void);
  *   "force_linear_walk"                  walk queries linearly instead of as spatial tiles
  *   "bwd_mode"                           1 = backward without the grad_value scatter, 2 = the scatter alone
  *   "debug_skip_scatter"                 same as bwd_mode 1
+ *   "bwd_deep"                           backward variant that issues a round's 32 row loads before their first use:
+ *                                        0 = automatic (launches with fewer passes than SMs), 1 = always, -1 = never
  * (the last two make results wrong on purpose: they exist to measure what bounds the backward).
  * Returns 0, or MSDA_ERR_INVALID_ARGUMENT for an unknown key. */
 int msda_set_option(const char *key, int value);

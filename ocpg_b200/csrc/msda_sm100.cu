@@ -52,6 +52,7 @@ std::atomic<int> g_unit{0};               // 0 = automatic; frames interleaved b
 std::atomic<int> g_force_generic{0};
 std::atomic<int> g_force_linear{0};     // experiments: never use the tiled query walk
 std::atomic<int> g_skip_scatter{0};     // experiments: see Dims::debug_skip_scatter
+std::atomic<int> g_bwd_deep{0};         // 0 = automatic (under-filled launches), 1 = always, -1 = never: msda_bwd_tiled<.., DEEP>
 
 int fail(int code, const char *msg) {
     snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -485,8 +486,8 @@ template <int WARPS> struct BwdSmem {
     float4 own[WARPS][32][2];   // per lane: its own point's bilinear weights; lx, ly, attention, corner validity
 };
 
-template <typename VT, int ROUNDS, int WARPS, bool FUSED>
-__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
+template <typename VT, int ROUNDS, int WARPS, bool FUSED, bool DEEP>
+__global__ void __launch_bounds__(WARPS * 32, DEEP ? 1 : 32 / WARPS)
 msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ start, const float *__restrict__ loc, const float *__restrict__ attn,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d,
@@ -577,20 +578,46 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
                 __syncwarp();
                 continue;
             }
+            if constexpr (DEEP) {
+                // Under-filled launch (the decoder's handful of queries): one or two warps per SM, so nothing hides a
+                // row load's latency except the warp's own loads -- issue all 32 row loads of the round before the first
+                // use (128 registers; this instantiation runs one CTA per SM), then scatter and reduce.
+                Row v[8][4];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const float4 pw = s_w[warp][grp][it];
-                const uint4 po = s_o[warp][grp][it];
-                const Row v00 = IO::load(row_at(vb, po.x));
-                const Row v01 = IO::load(row_at(vb, po.y));
-                const Row v10 = IO::load(row_at(vb, po.z));
-                const Row v11 = IO::load(row_at(vb, po.w));
-                // scatter: grad_value[corner] += (a * w_corner) * grad_out                  (cuh:125,134,143,152)
-                red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
-                red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
-                red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
-                red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
-                s_p[warp][grp][it][cl] = make_float4(dot_row(go, v00), dot_row(go, v01), dot_row(go, v10), dot_row(go, v11));
+                for (int it = 0; it < 8; ++it) {
+                    const uint4 po = s_o[warp][grp][it];
+                    v[it][0] = IO::load(row_at(vb, po.x));
+                    v[it][1] = IO::load(row_at(vb, po.y));
+                    v[it][2] = IO::load(row_at(vb, po.z));
+                    v[it][3] = IO::load(row_at(vb, po.w));
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const float4 pw = s_w[warp][grp][it];
+                    const uint4 po = s_o[warp][grp][it];
+                    red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
+                    red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
+                    red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
+                    red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
+                    s_p[warp][grp][it][cl] = make_float4(dot_row(go, v[it][0]), dot_row(go, v[it][1]), dot_row(go, v[it][2]),
+                                                         dot_row(go, v[it][3]));
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const float4 pw = s_w[warp][grp][it];
+                    const uint4 po = s_o[warp][grp][it];
+                    const Row v00 = IO::load(row_at(vb, po.x));
+                    const Row v01 = IO::load(row_at(vb, po.y));
+                    const Row v10 = IO::load(row_at(vb, po.z));
+                    const Row v11 = IO::load(row_at(vb, po.w));
+                    // scatter: grad_value[corner] += (a * w_corner) * grad_out                  (cuh:125,134,143,152)
+                    red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
+                    red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
+                    red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
+                    red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
+                    s_p[warp][grp][it][cl] = make_float4(dot_row(go, v00), dot_row(go, v01), dot_row(go, v10), dot_row(go, v11));
+                }
             }
             __syncwarp();
             // this lane owns point `pt`: add the 8 lanes' partials (rotated start: no bank conflicts)
@@ -873,19 +900,33 @@ int launch_fwd_tiled(const VT *value, const int64_t *shapes, const int64_t *star
     }
 }
 
+template <typename VT, int ROUNDS, int WARPS, bool DEEP>
+int launch_bwd_kernel(int grid, const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
+                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
+    const size_t smem = sizeof(BwdSmem<WARPS>);
+    if (fa) {
+        if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS, true, DEEP>, smem)) return rc;
+        msda_bwd_tiled<VT, ROUNDS, WARPS, true, DEEP><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, *fa);
+    } else {
+        if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS, false, DEEP>, smem)) return rc;
+        msda_bwd_tiled<VT, ROUNDS, WARPS, false, DEEP><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, FusedArgs{});
+    }
+    return after_launch("msda_bwd_tiled");
+}
+
+// The decoder's shapes (a handful of queries per frame) give fewer passes than one wave has CTAs: those launches use
+// the DEEP instantiation (8 warps, one CTA per SM, every row load of a round in flight at once).
 template <typename VT, int ROUNDS, int WARPS>
 int launch_bwd_one(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
                    const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
-    const size_t smem = sizeof(BwdSmem<WARPS>);
     const int grid = grid_for(32 / WARPS, g_bwd_ctas_per_sm);
-    if (fa) {
-        if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS, true>, smem)) return rc;
-        msda_bwd_tiled<VT, ROUNDS, WARPS, true><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, *fa);
-    } else {
-        if (const int rc = configure(msda_bwd_tiled<VT, ROUNDS, WARPS, false>, smem)) return rc;
-        msda_bwd_tiled<VT, ROUNDS, WARPS, false><<<grid, WARPS * 32, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, FusedArgs{});
+    if constexpr (WARPS == 8) {
+        const int64_t passes = (int64_t)d.N * d.M * ((d.Lq + Tile<8>::kQueries - 1) / Tile<8>::kQueries);   // linear walk
+        const int deep = g_bwd_deep.load();
+        if (deep > 0 || (deep == 0 && passes <= 2 * (int64_t)sm_count()))
+            return launch_bwd_kernel<VT, ROUNDS, 8, true>(sm_count(), go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
     }
-    return after_launch("msda_bwd_tiled");
+    return launch_bwd_kernel<VT, ROUNDS, WARPS, false>(grid, go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
 }
 
 template <typename VT, int ROUNDS>
@@ -964,6 +1005,7 @@ int msda_set_option(const char *key, int value) {
     if (!strcmp(key, "force_generic")) { g_force_generic = value; return MSDA_OK; }
     if (!strcmp(key, "force_linear_walk")) { g_force_linear = value; return MSDA_OK; }
     if (!strcmp(key, "debug_skip_scatter")) { g_skip_scatter = value; return MSDA_OK; }
+    if (!strcmp(key, "bwd_deep")) { g_bwd_deep = value; return MSDA_OK; }
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_set_option: unknown key");
 }
 
