@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SRC = os.path.join(_PKG, "csrc", "msda_sm100.cu")
 INCLUDE = os.path.join(_ROOT, "include")
-LIB_PATH = os.path.join(_PKG, "lib", "libmsda_sm100.so")
+LIB_PATH = os.environ.get("MSDA_LIB") or os.path.join(_PKG, "lib", "libmsda_sm100.so")   # MSDA_LIB: experiments
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

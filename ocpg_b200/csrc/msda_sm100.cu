@@ -482,12 +482,17 @@ template <int WARPS> struct BwdSmem {
     LevelTable lt;
     float4 w[WARPS][4][9];      // a*w00, a*w01, a*w10, a*w11   (scatter weights), one round
     uint4 o[WARPS][4][9];       // unit offsets of the four corners
-    float4 p[WARPS][4][8][8];   // [point][lane]: that lane's partial p00, p01, p10, p11
     float4 own[WARPS][32][2];   // per lane: its own point's bilinear weights; lx, ly, attention, corner validity
 };
 
+#ifndef MSDA_BWD_MINB8
+#define MSDA_BWD_MINB8 3      // resident 8-warp backward CTAs per SM the register budget is set for (3 -> 85 registers)
+#endif
+#ifndef MSDA_BWD_MINB16
+#define MSDA_BWD_MINB16 2
+#endif
 template <typename VT, int ROUNDS, int WARPS, bool FUSED, bool DEEP>
-__global__ void __launch_bounds__(WARPS * 32, DEEP ? 1 : 32 / WARPS)
+__global__ void __launch_bounds__(WARPS * 32, DEEP ? 1 : (WARPS == 8 ? MSDA_BWD_MINB8 : MSDA_BWD_MINB16))
 msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ start, const float *__restrict__ loc, const float *__restrict__ attn,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d,
@@ -499,7 +504,6 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
     LevelTable &lt = sm.lt;
     auto &s_w = sm.w;
     auto &s_o = sm.o;
-    auto &s_p = sm.p;
     auto &s_own = sm.own;
     load_level_table<WARPS>(lt, shapes, start, d.L, d.Lq);
     const bool tiled = d.tiled && lt.dense;
@@ -578,54 +582,65 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
                 __syncwarp();
                 continue;
             }
+            // One step = one point: 4 row loads, 4 predicated reds, the lane's partial dot products (its 4 channels).
+            auto step_rows = [&](int it, Row (&v)[4]) {
+                const uint4 po = s_o[warp][grp][it];
+                v[0] = IO::load(row_at(vb, po.x));
+                v[1] = IO::load(row_at(vb, po.y));
+                v[2] = IO::load(row_at(vb, po.z));
+                v[3] = IO::load(row_at(vb, po.w));
+            };
+            auto step_finish = [&](int it, const Row (&v)[4]) -> float4 {
+                const float4 pw = s_w[warp][grp][it];
+                const uint4 po = s_o[warp][grp][it];
+                // scatter: grad_value[corner] += (a * w_corner) * grad_out                  (cuh:125,134,143,152)
+                red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
+                red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
+                red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
+                red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
+                return make_float4(dot_row(go, v[0]), dot_row(go, v[1]), dot_row(go, v[2]), dot_row(go, v[3]));
+            };
+            // Reduce-scatter of the partials over the 8 lanes of a group by butterfly shuffles: after the exchange
+            // with mask 4, 2, 1 lane `cl` holds the sums of point `cl`.  No shared memory: the 32 KB transposition
+            // buffer of the first version left the L1 at its 28 KB minimum (four 50 KB CTAs per SM) and the gather
+            // at a 38 % hit rate.  exchange(): the half of the group with the mask bit clear keeps A, the other keeps B.
+            auto exchange = [&](const float4 &A, const float4 &B, int mask) -> float4 {
+                const bool up = (cl & mask) != 0;
+                const float4 send = up ? A : B;
+                float4 keep = up ? B : A;
+                keep.x += __shfl_xor_sync(0xffffffffu, send.x, mask);
+                keep.y += __shfl_xor_sync(0xffffffffu, send.y, mask);
+                keep.z += __shfl_xor_sync(0xffffffffu, send.z, mask);
+                keep.w += __shfl_xor_sync(0xffffffffu, send.w, mask);
+                return keep;
+            };
+            float4 qs;
             if constexpr (DEEP) {
                 // Under-filled launch (the decoder's handful of queries): one or two warps per SM, so nothing hides a
                 // row load's latency except the warp's own loads -- issue all 32 row loads of the round before the first
                 // use (128 registers; this instantiation runs one CTA per SM), then scatter and reduce.
                 Row v[8][4];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const uint4 po = s_o[warp][grp][it];
-                    v[it][0] = IO::load(row_at(vb, po.x));
-                    v[it][1] = IO::load(row_at(vb, po.y));
-                    v[it][2] = IO::load(row_at(vb, po.z));
-                    v[it][3] = IO::load(row_at(vb, po.w));
-                }
+                for (int it = 0; it < 8; ++it) step_rows(it, v[it]);
+                float4 k1[4];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const float4 pw = s_w[warp][grp][it];
-                    const uint4 po = s_o[warp][grp][it];
-                    red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
-                    red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
-                    red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
-                    red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
-                    s_p[warp][grp][it][cl] = make_float4(dot_row(go, v[it][0]), dot_row(go, v[it][1]), dot_row(go, v[it][2]),
-                                                         dot_row(go, v[it][3]));
-                }
+                for (int j = 0; j < 4; ++j) k1[j] = exchange(step_finish(j, v[j]), step_finish(j + 4, v[j + 4]), 4);
+                qs = exchange(exchange(k1[0], k1[2], 2), exchange(k1[1], k1[3], 2), 1);
             } else {
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const float4 pw = s_w[warp][grp][it];
-                    const uint4 po = s_o[warp][grp][it];
-                    const Row v00 = IO::load(row_at(vb, po.x));
-                    const Row v01 = IO::load(row_at(vb, po.y));
-                    const Row v10 = IO::load(row_at(vb, po.z));
-                    const Row v11 = IO::load(row_at(vb, po.w));
-                    // scatter: grad_value[corner] += (a * w_corner) * grad_out                  (cuh:125,134,143,152)
-                    red_row(row_at(gb, po.x), pw.x, go, scatter && pw.x != 0.f);
-                    red_row(row_at(gb, po.y), pw.y, go, scatter && pw.y != 0.f);
-                    red_row(row_at(gb, po.z), pw.z, go, scatter && pw.z != 0.f);
-                    red_row(row_at(gb, po.w), pw.w, go, scatter && pw.w != 0.f);
-                    s_p[warp][grp][it][cl] = make_float4(dot_row(go, v00), dot_row(go, v01), dot_row(go, v10), dot_row(go, v11));
-                }
-            }
-            __syncwarp();
-            // this lane owns point `pt`: add the 8 lanes' partials (rotated start: no bank conflicts)
-            float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float4 p = s_p[warp][grp][cl][(k + cl) & 7];
-                qs.x += p.x; qs.y += p.y; qs.z += p.z; qs.w += p.w;
+                // points in the order (0,4) (2,6) | (1,5) (3,7): each pair is exchanged as soon as it is complete, so at
+                // most two reduced float4 are live next to the point being gathered
+                auto pair = [&](int j) -> float4 {
+                    Row v[4];
+                    step_rows(j, v);
+                    const float4 A = step_finish(j, v);
+                    step_rows(j + 4, v);
+                    const float4 B = step_finish(j + 4, v);
+                    return exchange(A, B, 4);
+                };
+                const float4 e0 = pair(0);
+                const float4 k2a = exchange(e0, pair(2), 2);
+                const float4 e1 = pair(1);
+                qs = exchange(k2a, exchange(e1, pair(3), 2), 1);
             }
             if (q >= 0 && pt < pts) {
                 const float4 ow = s_own[warp][lane][0], og = s_own[warp][lane][1];
@@ -919,7 +934,7 @@ int launch_bwd_kernel(int grid, const VT *go, const VT *value, const int64_t *sh
 template <typename VT, int ROUNDS, int WARPS>
 int launch_bwd_one(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
                    const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
-    const int grid = grid_for(32 / WARPS, g_bwd_ctas_per_sm);
+    const int grid = grid_for(WARPS == 8 ? MSDA_BWD_MINB8 : MSDA_BWD_MINB16, g_bwd_ctas_per_sm);
     if constexpr (WARPS == 8) {
         const int64_t passes = (int64_t)d.N * d.M * ((d.Lq + Tile<8>::kQueries - 1) / Tile<8>::kQueries);   // linear walk
         const int deep = g_bwd_deep.load();
