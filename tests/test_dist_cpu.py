@@ -66,7 +66,7 @@ def _reducer_worker(rank, world, port, q):
         h = torch.tanh(l(h))
     h.sum().backward()
     nbytes = red.finish()
-    q.put((rank, [p.grad.clone() for p in layers.parameters()], x, nbytes))
+    q.put((rank, [p.grad.tolist() for p in layers.parameters()], x.tolist(), nbytes))     # plain lists: no shared-memory handles
     D.finalize()
 
 
@@ -85,7 +85,7 @@ def test_bucketed_grad_allreduce_gloo():
     torch.manual_seed(0)
     layers = torch.nn.ModuleList([torch.nn.Linear(6, 6) for _ in range(3)])
     for _, _, x, _ in res:
-        h = x
+        h = torch.tensor(x)
         for l in layers:
             h = torch.tanh(l(h))
         (h.sum() / 2).backward()                              # average over the 2 ranks
@@ -93,4 +93,4 @@ def test_bucketed_grad_allreduce_gloo():
     for rank, grads, _, nbytes in res:
         assert nbytes == sum(p.numel() for p in layers.parameters()) * 4
         for g, w in zip(grads, want):
-            assert torch.allclose(g, w, rtol=1e-5, atol=1e-6), rank
+            assert torch.allclose(torch.tensor(g), w, rtol=1e-5, atol=1e-6), rank
