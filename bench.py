@@ -92,43 +92,68 @@ def hbm_peak():
 # clocks sampling (nvidia-smi in the background during the timed region)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (every ~2 ms; the timed
+    region of the default run is ~70 ms, too short for `nvidia-smi -lms`), `nvidia-smi` only as a fallback."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.proc = None
+        import threading
+        self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as e:                       # no NVML: one nvidia-smi query at stop()
+            self.err = repr(e)
+            self.index = index
+
+    def _sample(self):
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
-                continue
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                self._sample()
+            except Exception:
+                pass
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml thread, 2 ms"}
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "samples": 1,
+                    "reasons": sorted(n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")),
+                    "source": "nvidia-smi after the timed region (NVML unavailable: %s)" % self.err}
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable: %r" % e]}
 
 
 # ----------------------------------------------------------------------------------------------
