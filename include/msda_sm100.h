@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 2
+#define MSDA_ABI_VERSION 3
 
 #define MSDA_OK 0
 #define MSDA_ERR_INVALID_ARGUMENT (-1) /* null pointer, non-positive dimension, misaligned pointer */
@@ -144,6 +144,29 @@ int msda_fused_backward_bf16(const uint16_t *grad_output, const uint16_t *value,
                              int num_query, int num_point,
                              float *grad_value_f32, uint16_t *grad_value_bf16, float *grad_offsets, float *grad_logits,
                              float *grad_sampling_loc_out, msda_stream_t stream);
+
+/* ---- encoder layer epilogue (new).  The elementwise / reduction work of
+ *      DeformableTransformerEncoderLayer around the attention and the FFN (models/deformable_transformer.py:243-260)
+ *      as HBM-streaming kernels:
+ *        forward   z = (x + bias) + residual ;  y = LayerNorm(z) * gamma + beta        (:253-254, :246-247)
+ *                  x, residual, z, y: [rows][channels]; bias (may be NULL), gamma, beta: [channels];
+ *                  mean, rstd: [rows] (saved for the backward); channels in {128, 256, 512, 1024}
+ *        backward  dz = d x = d residual, grad_gamma, grad_beta, grad_bias (NULL = not wanted) -- the three
+ *                  [channels] outputs are zero-filled by the call and accumulated with fp32 reds
+ *        msda_column_sum_f32                out[c] = sum_r x[r][c]: the bias gradient of a Linear (channels % 4 == 0)
+ *        msda_relu_backward_column_sum_f32  dpre = dh * (h > 0) and dbias = column sum of dpre, h = the ReLU output ---- */
+int msda_epilogue_ln_forward_f32(const float *x, const float *bias, const float *residual, const float *gamma,
+                                 const float *beta, float eps, int64_t rows, int channels,
+                                 float *z, float *y, float *mean, float *rstd, msda_stream_t stream);
+
+int msda_epilogue_ln_backward_f32(const float *dy, const float *z, const float *mean, const float *rstd,
+                                  const float *gamma, int64_t rows, int channels,
+                                  float *dz, float *grad_gamma, float *grad_beta, float *grad_bias, msda_stream_t stream);
+
+int msda_column_sum_f32(const float *x, int64_t rows, int channels, float *out, msda_stream_t stream);
+
+int msda_relu_backward_column_sum_f32(const float *dh, const float *h, int64_t rows, int channels,
+                                      float *dpre, float *dbias, msda_stream_t stream);
 
 /* Which kernel a call with these dimensions runs: 1 = the sm_100a tiled kernel (channels == 32,
  * num_levels <= 16, num_levels*num_point <= 32), 0 = the generic kernel (any shape).  For tests and

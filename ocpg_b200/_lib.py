@@ -26,7 +26,8 @@ SYMBOLS = [
     "msda_abi_version", "msda_last_error", "msda_forward_f32", "msda_backward_f32", "msda_forward_f64",
     "msda_backward_f64", "msda_forward_bf16", "msda_backward_bf16", "msda_kernel_plan", "msda_launch_count",
     "msda_set_option", "msda_fused_forward_f32", "msda_fused_backward_f32", "msda_fused_forward_bf16",
-    "msda_fused_backward_bf16",
+    "msda_fused_backward_bf16", "msda_epilogue_ln_forward_f32", "msda_epilogue_ln_backward_f32", "msda_column_sum_f32",
+    "msda_relu_backward_column_sum_f32",
 ]
 
 _lib = None
@@ -42,7 +43,7 @@ def _nvcc() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/msda_sm100.cu for sm_100a into ocpg_b200/lib/libmsda_sm100.so (cross-compiles
     without a GPU).  Rebuilds when the source or header is newer than the library."""
-    deps = [SRC, os.path.join(INCLUDE, "msda_sm100.h")]
+    deps = [SRC, os.path.join(_PKG, "csrc", "msda_epilogue.cuh"), os.path.join(INCLUDE, "msda_sm100.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
         os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
@@ -96,7 +97,16 @@ def lib() -> ctypes.CDLL:
         b.restype = c_int
         n_out = 5 if sfx == "bf16" else 4
         b.argtypes = [c_void_p] * 7 + [c_int] + dims + [c_void_p] * n_out + [c_void_p]
-    if L.msda_abi_version() != 2:
+    from ctypes import c_float, c_int64
+    L.msda_epilogue_ln_forward_f32.restype = c_int
+    L.msda_epilogue_ln_forward_f32.argtypes = [c_void_p] * 5 + [c_float, c_int64, c_int] + [c_void_p] * 4 + [c_void_p]
+    L.msda_epilogue_ln_backward_f32.restype = c_int
+    L.msda_epilogue_ln_backward_f32.argtypes = [c_void_p] * 5 + [c_int64, c_int] + [c_void_p] * 4 + [c_void_p]
+    L.msda_column_sum_f32.restype = c_int
+    L.msda_column_sum_f32.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
+    L.msda_relu_backward_column_sum_f32.restype = c_int
+    L.msda_relu_backward_column_sum_f32.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    if L.msda_abi_version() != 3:
         raise RuntimeError("libmsda_sm100.so ABI version mismatch")
     _lib = L
     return L

@@ -701,6 +701,8 @@ __global__ void msda_f32_to_bf16(const float4 *__restrict__ src, uint2 *__restri
     }
 }
 
+#include "msda_epilogue.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // Generic kernels: any D, L, P; float or double.  Correctness path for the shapes the tiled kernels
 // do not cover (the reference's tests use D in {30, 32, 64, 71, 1025, 2048, 3096} in fp64, test.py:85).
@@ -1217,6 +1219,102 @@ int msda_fused_backward_bf16(const uint16_t *go, const uint16_t *value, const in
         return after_launch("msda_f32_to_bf16");
     }
     return MSDA_OK;
+}
+
+}  // extern "C"
+
+// ---- encoder layer epilogue: bias + residual + LayerNorm, Linear bias gradients ----
+namespace {
+template <int VEC>
+int launch_ln_fwd(const float *x, const float *bias, const float *res, const float *gamma, const float *beta, float eps,
+                  int64_t rows, float *z, float *y, float *mean, float *rstd, cudaStream_t st) {
+    const int64_t want = (rows + 7) / 8;
+    const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+    epilogue_ln_fwd<VEC><<<grid, 256, 0, st>>>(x, bias, res, gamma, beta, eps, rows, z, y, mean, rstd);
+    return after_launch("epilogue_ln_fwd");
+}
+template <int VEC>
+int launch_ln_bwd(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma, int64_t rows,
+                  float *dz, float *dgamma, float *dbeta, float *dbias, cudaStream_t st) {
+    const int64_t want = (rows + 7) / 8;
+    const int grid = (int)(want < (int64_t)sm_count() * 2 ? want : (int64_t)sm_count() * 2);
+    epilogue_ln_bwd<VEC><<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias);
+    return after_launch("epilogue_ln_bwd");
+}
+int zero_fill(float *p, int64_t n, cudaStream_t st, const char *what) {
+    if (!p || n <= 0) return MSDA_OK;
+    const cudaError_t e = cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, st);
+    return e == cudaSuccess ? MSDA_OK : fail_cuda(e, what);
+}
+int column_sum_any(bool relu, const float *x, const float *h, int64_t rows, int C, float *dpre, float *out, cudaStream_t st) {
+    if (rows < 0 || C <= 0 || (C & 3)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: channels must be a positive multiple of 4");
+    if (!out) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: null output");
+    if (const int rc = zero_fill(out, C, st, "msda_column_sum: memset")) return rc;
+    if (rows == 0) return MSDA_OK;
+    if (!x || (relu && (!h || !dpre))) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: null pointer");
+    if (misaligned(x, 16) || (relu && (misaligned(h, 16) || misaligned(dpre, 16))))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: pointers must be 16-byte aligned");
+    const int64_t want = (rows + 15) / 16;
+    const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+    const size_t smem = 256 * sizeof(float4);
+    if (relu) column_sum_kernel<true><<<grid, 256, smem, st>>>(x, h, rows, C, dpre, out);
+    else column_sum_kernel<false><<<grid, 256, smem, st>>>(x, nullptr, rows, C, nullptr, out);
+    return after_launch("column_sum_kernel");
+}
+}  // namespace
+
+extern "C" {
+
+int msda_epilogue_ln_forward_f32(const float *x, const float *bias, const float *residual, const float *gamma,
+                                 const float *beta, float eps, int64_t rows, int channels, float *z, float *y, float *mean,
+                                 float *rstd, msda_stream_t stream) {
+    if (rows < 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_forward_f32: negative row count");
+    if (rows == 0) return MSDA_OK;
+    if (!x || !residual || !gamma || !beta || !z || !y || !mean || !rstd)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_forward_f32: null pointer");
+    if (misaligned(x, 16) || misaligned(residual, 16) || misaligned(gamma, 16) || misaligned(beta, 16) || misaligned(z, 16) ||
+        misaligned(y, 16) || (bias && misaligned(bias, 16)))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_forward_f32: pointers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (channels) {
+        case 128: return launch_ln_fwd<1>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
+        case 256: return launch_ln_fwd<2>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
+        case 512: return launch_ln_fwd<4>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
+        case 1024: return launch_ln_fwd<8>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
+        default: return fail(MSDA_ERR_UNSUPPORTED, "msda_epilogue_ln_forward_f32: channels must be 128, 256, 512 or 1024");
+    }
+}
+
+int msda_epilogue_ln_backward_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
+                                  int64_t rows, int channels, float *dz, float *dgamma, float *dbeta, float *dbias,
+                                  msda_stream_t stream) {
+    if (rows < 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: negative row count");
+    if (channels != 128 && channels != 256 && channels != 512 && channels != 1024)
+        return fail(MSDA_ERR_UNSUPPORTED, "msda_epilogue_ln_backward_f32: channels must be 128, 256, 512 or 1024");
+    if (!dgamma || !dbeta) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: null grad_gamma / grad_beta");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (const int rc = zero_fill(dgamma, channels, st, "msda_epilogue_ln_backward_f32: memset")) return rc;
+    if (const int rc = zero_fill(dbeta, channels, st, "msda_epilogue_ln_backward_f32: memset")) return rc;
+    if (const int rc = zero_fill(dbias, channels, st, "msda_epilogue_ln_backward_f32: memset")) return rc;
+    if (rows == 0) return MSDA_OK;
+    if (!dy || !z || !mean || !rstd || !gamma || !dz) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: null pointer");
+    if (misaligned(dy, 16) || misaligned(z, 16) || misaligned(gamma, 16) || misaligned(dz, 16))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: pointers must be 16-byte aligned");
+    switch (channels) {
+        case 128: return launch_ln_bwd<1>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
+        case 256: return launch_ln_bwd<2>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
+        case 512: return launch_ln_bwd<4>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
+        default: return launch_ln_bwd<8>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
+    }
+}
+
+int msda_column_sum_f32(const float *x, int64_t rows, int channels, float *out, msda_stream_t stream) {
+    return column_sum_any(false, x, nullptr, rows, channels, nullptr, out, (cudaStream_t)stream);
+}
+
+int msda_relu_backward_column_sum_f32(const float *dh, const float *h, int64_t rows, int channels, float *dpre, float *dbias,
+                                      msda_stream_t stream) {
+    return column_sum_any(true, dh, h, rows, channels, dpre, dbias, (cudaStream_t)stream);
 }
 
 }  // extern "C"

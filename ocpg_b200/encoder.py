@@ -9,7 +9,10 @@ the rest of the model.
 
 Differences from the reference, all on the host side:
   * ``fused=True`` (default) switches every layer's MSDeformAttn to the fused kernels and stops it from
-    materialising sampling_locations / attention_weights, which the encoder throws away (:251);
+    materialising sampling_locations / attention_weights, which the encoder throws away (:251); it also runs the
+    layer's epilogue -- bias + residual + LayerNorm after the attention and after the FFN, the FFN's bias + ReLU and
+    every bias gradient -- through the streaming kernels of ocpg_b200/epilogue.py
+    whenever dropout is inactive (p == 0 or eval mode) and the activation is ReLU; otherwise the reference's graph;
   * the reference wraps the attention in ``autocast(enabled=False)`` (:250); so does this.
 """
 from __future__ import annotations
@@ -20,6 +23,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import epilogue
 from .modules import MSDeformAttn
 
 
@@ -37,6 +41,8 @@ class DeformableTransformerEncoderLayer(nn.Module):
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
         self.self_attn.fused = bool(fused)
         self.self_attn.emit_sampling = not fused
+        self.fused = bool(fused)
+        self.activation_name = activation
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = nn.LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_ffn)
@@ -54,7 +60,22 @@ class DeformableTransformerEncoderLayer(nn.Module):
         hidden = self.dropout2(self.activation(self.linear1(src)))
         return self.norm2(src + self.dropout3(self.linear2(hidden)))
 
+    def _epilogue_ok(self, src):
+        dropout_off = not self.training or max(self.dropout1.p, self.dropout2.p, self.dropout3.p) == 0.0
+        return (self.fused and dropout_off and self.activation_name == "relu" and src.shape[-1] in epilogue.LN_CHANNELS
+                and epilogue.supported(src, self.norm1.weight))
+
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        if self._epilogue_ok(src):
+            with torch.autocast(device_type=src.device.type, enabled=False):
+                core = self.self_attn.attend(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
+                                             level_start_index, padding_mask)[0]
+            proj = self.self_attn.output_proj
+            src = epilogue.bias_residual_layer_norm(F.linear(core, proj.weight), proj.bias, src, self.norm1.weight,
+                                                    self.norm1.bias, self.norm1.eps)             # :253-254
+            hidden = epilogue.linear_relu(src, self.linear1.weight, self.linear1.bias)           # :244
+            return epilogue.bias_residual_layer_norm(F.linear(hidden, self.linear2.weight), self.linear2.bias, src,
+                                                     self.norm2.weight, self.norm2.bias, self.norm2.eps)   # :245-247
         with torch.autocast(device_type=src.device.type, enabled=False):
             attn_out = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                                       level_start_index, padding_mask)[0]

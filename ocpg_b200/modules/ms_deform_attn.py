@@ -28,6 +28,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import MultiScaleDeformableAttention as MSDA
+from .. import epilogue
 from ..functions import MSDeformAttnFunction
 from ..functions.ms_deform_attn_func import MSDeformAttnFusedFunction
 
@@ -94,7 +95,16 @@ class MSDeformAttn(nn.Module):
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
-        """
+        """See attend(); applies ``output_proj`` (:116) to its first result."""
+        output, sampling_locations, weights = self.attend(query, reference_points, input_flatten, input_spatial_shapes,
+                                                          input_level_start_index, input_padding_mask)
+        return self.output_proj(output), sampling_locations, weights                     # :116, :118
+
+    def attend(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+               input_padding_mask=None):
+        """Everything of the reference's forward (:92-115) up to, not including, ``output_proj`` -- so that a caller can
+        fold that projection's bias into its own epilogue (ocpg_b200/encoder.py).
+
         :param query                    (N, Length_query, C)
         :param reference_points         (N, Length_query, n_levels, 2) in [0, 1], top-left (0,0), bottom-right (1,1),
                                         including padding area; or (N, Length_query, n_levels, 4) = boxes (cx, cy, w, h)
@@ -103,28 +113,30 @@ class MSDeformAttn(nn.Module):
         :param input_level_start_index  (n_levels,)
         :param input_padding_mask       (N, sum_l H_l*W_l), True for padding elements
 
-        :return (output (N, Length_query, C), sampling_locations (N, Lq, M, L, P, 2), attention_weights (N, Lq, M, L, P))
+        :return (output before output_proj (N, Length_query, C), sampling_locations (N, Lq, M, L, P, 2),
+                 attention_weights (N, Lq, M, L, P))
         """
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
         self._check_shapes(input_spatial_shapes, Len_in)
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
-        value = self.value_proj(input_flatten)                                           # :96
+        # fused mode: the Linears' bias gradients come from the streaming column-sum kernel (ocpg_b200/epilogue.py)
+        lin = (lambda layer, x: epilogue.linear(x, layer.weight, layer.bias)) if self.fused else (lambda layer, x: layer(x))
+        value = lin(self.value_proj, input_flatten)                                      # :96
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))           # :97-98
         value = value.view(N, Len_in, M, self.d_model // M)
-        offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)                # :100
+        offsets = lin(self.sampling_offsets, query).view(N, Len_q, M, L, P, 2)           # :100
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
                 reference_points.shape[-1]))
         if self.fused and value.is_cuda and MSDA.fused_supported(value, L, P):
-            logits = self.attention_weights(query).view(N, Len_q, M, L * P)
-            output, sampling_locations, weights = MSDeformAttnFusedFunction.apply(
+            logits = lin(self.attention_weights, query).view(N, Len_q, M, L * P)
+            return MSDeformAttnFusedFunction.apply(
                 value.contiguous(), input_spatial_shapes, input_level_start_index, offsets.contiguous(),
                 logits.contiguous(), reference_points.to(torch.float32).contiguous(), self.im2col_step, self.emit_sampling)
-            return self.output_proj(output), sampling_locations, weights
-        weights = F.softmax(self.attention_weights(query).view(N, Len_q, M, L * P), -1)  # :101-102
+        weights = F.softmax(lin(self.attention_weights, query).view(N, Len_q, M, L * P), -1)  # :101-102
         weights = weights.view(N, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:                                              # :104-107
             wh = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
@@ -137,5 +149,4 @@ class MSDeformAttn(nn.Module):
                 reference_points.shape[-1]))
         output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                             sampling_locations.contiguous(), weights.contiguous(), self.im2col_step)
-        output = self.output_proj(output)                                                # :116
-        return output, sampling_locations, weights                                       # :118
+        return output, sampling_locations, weights
