@@ -20,6 +20,10 @@ struct LaneRow {
     float4 v[VEC];
 };
 
+__device__ __forceinline__ void red_add_f32x4(float *p, const float4 &v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
@@ -119,9 +123,11 @@ __device__ __forceinline__ void flush_column_sums(const LaneRow<VEC> (&acc)[NACC
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) {
-        float *dst = out[i / C];
-        if (dst) atomicAdd(dst + (i % C), smem[i]);
+    // one 16-byte red per column chunk: every CTA of the grid adds into the same C addresses, and the L2 serialises
+    // same-address atomics, so their number (not their bytes) is what this flush costs
+    for (int i = threadIdx.x; i < NACC * (C / 4); i += blockDim.x) {
+        float *dst = out[i / (C / 4)];
+        if (dst) red_add_f32x4(dst + 4 * (i % (C / 4)), reinterpret_cast<const float4 *>(smem)[i]);
     }
 }
 
@@ -193,7 +199,7 @@ column_sum_kernel(const float *__restrict__ x, const float *__restrict__ mask_sr
         const int c = c0 + tx;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active && c < C4) {
-            for (int64_t r = r0 + ty; r < r1; r += rpp) {
+            auto take = [&](int64_t r) -> float4 {
                 float4 v;
                 const float4 *src = reinterpret_cast<const float4 *>(x) + r * C4 + c;
                 asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -207,7 +213,21 @@ column_sum_kernel(const float *__restrict__ x, const float *__restrict__ mask_sr
                     v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
                     reinterpret_cast<float4 *>(dpre)[r * C4 + c] = v;
                 }
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                return v;
+            };
+            // kU rows in flight per thread: a single 16-byte load per iteration leaves the kernel latency-bound
+            constexpr int kU = RELU ? 4 : 8;
+            int64_t r = r0 + ty;
+            for (; r + (kU - 1) * (int64_t)rpp < r1; r += kU * (int64_t)rpp) {
+                float4 a[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) a[u] = take(r + u * (int64_t)rpp);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) { acc.x += a[u].x; acc.y += a[u].y; acc.z += a[u].z; acc.w += a[u].w; }
+            }
+            for (; r < r1; r += rpp) {
+                const float4 a0 = take(r);
+                acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
             }
         }
         if (active) s_part[ty * cols + tx] = acc;
@@ -217,10 +237,7 @@ column_sum_kernel(const float *__restrict__ x, const float *__restrict__ mask_sr
                 const float4 p = s_part[k * cols + tx];
                 acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
             }
-            if (r0 < r1) {
-                atomicAdd(out + 4 * c + 0, acc.x); atomicAdd(out + 4 * c + 1, acc.y);
-                atomicAdd(out + 4 * c + 2, acc.z); atomicAdd(out + 4 * c + 3, acc.w);
-            }
+            if (r0 < r1) red_add_f32x4(out + 4 * c, acc);
         }
         __syncthreads();
     }

@@ -1252,10 +1252,11 @@ int column_sum_any(bool relu, const float *x, const float *h, int64_t rows, int 
     if (const int rc = zero_fill(out, C, st, "msda_column_sum: memset")) return rc;
     if (rows == 0) return MSDA_OK;
     if (!x || (relu && (!h || !dpre))) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: null pointer");
-    if (misaligned(x, 16) || (relu && (misaligned(h, 16) || misaligned(dpre, 16))))
+    if (misaligned(x, 16) || misaligned(out, 16) || (relu && (misaligned(h, 16) || misaligned(dpre, 16))))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: pointers must be 16-byte aligned");
-    const int64_t want = (rows + 15) / 16;
-    const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+    // few CTAs: each one ends with C/4 same-address reds, which the L2 serialises
+    const int64_t want = (rows + 31) / 32, cap = (int64_t)sm_count() * (relu ? 4 : 2);
+    const int grid = (int)(want < cap ? want : cap);
     const size_t smem = 256 * sizeof(float4);
     if (relu) column_sum_kernel<true><<<grid, 256, smem, st>>>(x, h, rows, C, dpre, out);
     else column_sum_kernel<false><<<grid, 256, smem, st>>>(x, nullptr, rows, C, nullptr, out);
@@ -1298,7 +1299,8 @@ int msda_epilogue_ln_backward_f32(const float *dy, const float *z, const float *
     if (const int rc = zero_fill(dbias, channels, st, "msda_epilogue_ln_backward_f32: memset")) return rc;
     if (rows == 0) return MSDA_OK;
     if (!dy || !z || !mean || !rstd || !gamma || !dz) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: null pointer");
-    if (misaligned(dy, 16) || misaligned(z, 16) || misaligned(gamma, 16) || misaligned(dz, 16))
+    if (misaligned(dy, 16) || misaligned(z, 16) || misaligned(gamma, 16) || misaligned(dz, 16) || misaligned(dgamma, 16) ||
+        misaligned(dbeta, 16) || (dbias && misaligned(dbias, 16)))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: pointers must be 16-byte aligned");
     switch (channels) {
         case 128: return launch_ln_bwd<1>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
