@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 3
+#define MSDA_ABI_VERSION 4
 
 #define MSDA_OK 0
 #define MSDA_ERR_INVALID_ARGUMENT (-1) /* null pointer, non-positive dimension, misaligned pointer */
@@ -167,6 +167,36 @@ int msda_column_sum_f32(const float *x, int64_t rows, int channels, float *out, 
 
 int msda_relu_backward_column_sum_f32(const float *dh, const float *h, int64_t rows, int channels,
                                       float *dpre, float *dbias, msda_stream_t stream);
+
+/* ---- the same epilogue with dropout ACTIVE (training: dropout1 / dropout2 / dropout3 of
+ *      DeformableTransformerEncoderLayer, models/deformable_transformer.py:226-235, p = 0.1 in opts.py).
+ *      The keep mask is never stored: it is Philox4x32-7 of (rng[0], rng[1], salt, index of the element's 4-float
+ *      chunk), `rng` = two 64-bit words in DEVICE memory (read by the kernel: safe to capture in a CUDA graph and
+ *      refresh between replays), `salt` = the call site.  keep <=> 32-bit word >= floor(p * 2^32), 0 <= p < 1;
+ *      kept elements are scaled by 1 / (1 - p) like torch.nn.functional.dropout.
+ *        msda_epilogue_ln_dropout_forward_f32    z = dropout(x + bias) + residual ; y = LayerNorm(z)
+ *        msda_epilogue_ln_dropout_backward_f32   dz = d residual, dx = dz * keep / (1 - p) = d x, grad_bias = column sum of dx
+ *        msda_dropout_inplace_f32                h *= keep / (1 - p) in place, n = element count (multiple of 4)
+ *        msda_relu_dropout_backward_column_sum_f32   for h_dropped = dropout(relu(pre)): dpre = dh * (h_dropped > 0) / (1 - p)
+ *                                                (h_dropped > 0 <=> pre > 0 and kept: no mask needed) and its column sum
+ *        msda_dropout_mask_u8                    the keep mask itself, one byte per element (tests only) ---- */
+int msda_epilogue_ln_dropout_forward_f32(const float *x, const float *bias, const float *residual, const float *gamma,
+                                         const float *beta, float eps, int64_t rows, int channels,
+                                         const void *rng, uint32_t salt, float p,
+                                         float *z, float *y, float *mean, float *rstd, msda_stream_t stream);
+
+int msda_epilogue_ln_dropout_backward_f32(const float *dy, const float *z, const float *mean, const float *rstd,
+                                          const float *gamma, int64_t rows, int channels,
+                                          const void *rng, uint32_t salt, float p,
+                                          float *dz, float *dx, float *grad_gamma, float *grad_beta, float *grad_bias,
+                                          msda_stream_t stream);
+
+int msda_dropout_inplace_f32(float *h, int64_t n, const void *rng, uint32_t salt, float p, msda_stream_t stream);
+
+int msda_relu_dropout_backward_column_sum_f32(const float *dh, const float *h_dropped, float p, int64_t rows, int channels,
+                                              float *dpre, float *dbias, msda_stream_t stream);
+
+int msda_dropout_mask_u8(const void *rng, uint32_t salt, float p, int64_t n, uint8_t *keep, msda_stream_t stream);
 
 /* Which kernel a call with these dimensions runs: 1 = the sm_100a tiled kernel (channels == 32,
  * num_levels <= 16, num_levels*num_point <= 32), 0 = the generic kernel (any shape).  For tests and

@@ -27,7 +27,8 @@ SYMBOLS = [
     "msda_backward_f64", "msda_forward_bf16", "msda_backward_bf16", "msda_kernel_plan", "msda_launch_count",
     "msda_set_option", "msda_fused_forward_f32", "msda_fused_backward_f32", "msda_fused_forward_bf16",
     "msda_fused_backward_bf16", "msda_epilogue_ln_forward_f32", "msda_epilogue_ln_backward_f32", "msda_column_sum_f32",
-    "msda_relu_backward_column_sum_f32",
+    "msda_relu_backward_column_sum_f32", "msda_epilogue_ln_dropout_forward_f32", "msda_epilogue_ln_dropout_backward_f32",
+    "msda_dropout_inplace_f32", "msda_relu_dropout_backward_column_sum_f32", "msda_dropout_mask_u8",
 ]
 
 _lib = None
@@ -106,7 +107,20 @@ def lib() -> ctypes.CDLL:
     L.msda_column_sum_f32.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
     L.msda_relu_backward_column_sum_f32.restype = c_int
     L.msda_relu_backward_column_sum_f32.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
-    if L.msda_abi_version() != 3:
+    from ctypes import c_uint32
+    L.msda_epilogue_ln_dropout_forward_f32.restype = c_int
+    L.msda_epilogue_ln_dropout_forward_f32.argtypes = ([c_void_p] * 5 + [c_float, c_int64, c_int] + [c_void_p, c_uint32, c_float]
+                                                       + [c_void_p] * 4 + [c_void_p])
+    L.msda_epilogue_ln_dropout_backward_f32.restype = c_int
+    L.msda_epilogue_ln_dropout_backward_f32.argtypes = ([c_void_p] * 5 + [c_int64, c_int] + [c_void_p, c_uint32, c_float]
+                                                        + [c_void_p] * 5 + [c_void_p])
+    L.msda_dropout_inplace_f32.restype = c_int
+    L.msda_dropout_inplace_f32.argtypes = [c_void_p, c_int64, c_void_p, c_uint32, c_float, c_void_p]
+    L.msda_relu_dropout_backward_column_sum_f32.restype = c_int
+    L.msda_relu_dropout_backward_column_sum_f32.argtypes = [c_void_p, c_void_p, c_float, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    L.msda_dropout_mask_u8.restype = c_int
+    L.msda_dropout_mask_u8.argtypes = [c_void_p, c_uint32, c_float, c_int64, c_void_p, c_void_p]
+    if L.msda_abi_version() != 4:
         raise RuntimeError("libmsda_sm100.so ABI version mismatch")
     _lib = L
     return L

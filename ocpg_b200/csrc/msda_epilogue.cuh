@@ -55,13 +55,53 @@ __device__ __forceinline__ void store_row(float *p, int lane, const LaneRow<VEC>
     for (int k = 0; k < VEC; ++k) reinterpret_cast<float4 *>(p)[lane + 32 * k] = r.v[k];
 }
 
-// y = LayerNorm(x + bias + residual) * gamma + beta; also writes z (the pre-norm sum) and the row statistics.
-template <int VEC>
+// ---- dropout (deformable_transformer.py:226-235: dropout1 / dropout2 / dropout3, p = 0.1 in training) ----
+// The keep mask is never stored: it is a pure function of (rng[0], rng[1], salt, element index) -- Philox4x32-7, one
+// call per float4 chunk -- so the backward regenerates it.  `rng` points at two 64-bit words in device memory (drawn by
+// the caller from torch's CUDA generator: reproducible under torch.manual_seed, and a captured CUDA graph sees fresh
+// words on every replay); `salt` tells the call sites of one layer apart.  keep <=> word >= p * 2^32.
+struct DropoutArgs {
+    const uint64_t *rng;
+    uint32_t salt;
+    uint32_t thresh;     // floor(p * 2^32)
+    float scale;         // 1 / (1 - p)
+};
+struct DropoutKey {
+    uint2 key;
+    uint32_t c2, c3;
+};
+__device__ __forceinline__ DropoutKey dropout_key(const DropoutArgs &da) {
+    const uint64_t a = __ldg(da.rng), b = __ldg(da.rng + 1);
+    return DropoutKey{make_uint2((uint32_t)a, (uint32_t)(a >> 32)), (uint32_t)b ^ da.salt, (uint32_t)(b >> 32)};
+}
+__device__ __forceinline__ uint4 philox4x32_7(uint2 key, uint4 c) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// keep * scale for the four elements of float4 chunk `chunk` (a global chunk index)
+__device__ __forceinline__ float4 dropout_factor(const DropoutKey &k, const DropoutArgs &da, int64_t chunk) {
+    const uint4 r = philox4x32_7(k.key, make_uint4((uint32_t)chunk, (uint32_t)((uint64_t)chunk >> 32), k.c2, k.c3));
+    return make_float4(r.x >= da.thresh ? da.scale : 0.f, r.y >= da.thresh ? da.scale : 0.f,
+                       r.z >= da.thresh ? da.scale : 0.f, r.w >= da.thresh ? da.scale : 0.f);
+}
+
+// y = LayerNorm(dropout(x + bias) + residual) * gamma + beta; also writes z (the pre-norm sum) and the row statistics.
+template <int VEC, bool DROP>
 __global__ void __launch_bounds__(256)
 epilogue_ln_fwd(const float *__restrict__ x, const float *__restrict__ bias, const float *__restrict__ residual,
                 const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int64_t rows,
-                float *__restrict__ z_out, float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out) {
+                float *__restrict__ z_out, float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                DropoutArgs da) {
     constexpr int C = 128 * VEC;
+    DropoutKey dk{};
+    if constexpr (DROP) dk = dropout_key(da);
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const LaneRow<VEC> g = load_row<VEC>(gamma, lane), b = load_row<VEC>(beta, lane);
@@ -74,10 +114,18 @@ epilogue_ln_fwd(const float *__restrict__ x, const float *__restrict__ bias, con
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            z.v[k].x = (z.v[k].x + bi.v[k].x) + res.v[k].x;       // torch's order: (x + bias) + residual
-            z.v[k].y = (z.v[k].y + bi.v[k].y) + res.v[k].y;
-            z.v[k].z = (z.v[k].z + bi.v[k].z) + res.v[k].z;
-            z.v[k].w = (z.v[k].w + bi.v[k].w) + res.v[k].w;
+            if constexpr (DROP) {                                   // residual + dropout(x + bias)
+                const float4 f = dropout_factor(dk, da, r * (C / 4) + lane + 32 * k);
+                z.v[k].x = __fmul_rn(z.v[k].x + bi.v[k].x, f.x) + res.v[k].x;
+                z.v[k].y = __fmul_rn(z.v[k].y + bi.v[k].y, f.y) + res.v[k].y;
+                z.v[k].z = __fmul_rn(z.v[k].z + bi.v[k].z, f.z) + res.v[k].z;
+                z.v[k].w = __fmul_rn(z.v[k].w + bi.v[k].w, f.w) + res.v[k].w;
+            } else {
+                z.v[k].x = (z.v[k].x + bi.v[k].x) + res.v[k].x;       // torch's order: (x + bias) + residual
+                z.v[k].y = (z.v[k].y + bi.v[k].y) + res.v[k].y;
+                z.v[k].z = (z.v[k].z + bi.v[k].z) + res.v[k].z;
+                z.v[k].w = (z.v[k].w + bi.v[k].w) + res.v[k].w;
+            }
             s += (z.v[k].x + z.v[k].y) + (z.v[k].z + z.v[k].w);
         }
         const float mean = warp_sum(s) * (1.f / C);
@@ -133,12 +181,16 @@ __device__ __forceinline__ void flush_column_sums(const LaneRow<VEC> (&acc)[NACC
 
 // dz = rstd * (g - mean(g) - zh * mean(g * zh)),  g = dy * gamma, zh = (z - mean) * rstd;  d gamma += dy * zh,
 // d beta += dy, d bias += dz (outputs zero-filled by the launcher).
-template <int VEC>
+// With DROP: dz is the residual's gradient, dx_out = dz * keep / (1 - p) the Linear output's, and d bias sums dx.
+template <int VEC, bool DROP>
 __global__ void __launch_bounds__(256)
 epilogue_ln_bwd(const float *__restrict__ dy, const float *__restrict__ z, const float *__restrict__ mean_in,
                 const float *__restrict__ rstd_in, const float *__restrict__ gamma, int64_t rows, float *__restrict__ dz_out,
-                float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias) {
+                float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, float *__restrict__ dx_out,
+                DropoutArgs da) {
     constexpr int C = 128 * VEC;
+    DropoutKey dk{};
+    if constexpr (DROP) dk = dropout_key(da);
     __shared__ __align__(16) float s_cols[3 * C];
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -172,7 +224,14 @@ epilogue_ln_bwd(const float *__restrict__ dy, const float *__restrict__ z, const
             acc[0].v[k].x += d.v[k].x * zh.v[k].x; acc[0].v[k].y += d.v[k].y * zh.v[k].y;
             acc[0].v[k].z += d.v[k].z * zh.v[k].z; acc[0].v[k].w += d.v[k].w * zh.v[k].w;
             acc[1].v[k].x += d.v[k].x; acc[1].v[k].y += d.v[k].y; acc[1].v[k].z += d.v[k].z; acc[1].v[k].w += d.v[k].w;
-            acc[2].v[k].x += o.v[k].x; acc[2].v[k].y += o.v[k].y; acc[2].v[k].z += o.v[k].z; acc[2].v[k].w += o.v[k].w;
+            if constexpr (DROP) {
+                const float4 f = dropout_factor(dk, da, r * (C / 4) + lane + 32 * k);
+                const float4 dx = make_float4(o.v[k].x * f.x, o.v[k].y * f.y, o.v[k].z * f.z, o.v[k].w * f.w);
+                reinterpret_cast<float4 *>(dx_out + r * C)[lane + 32 * k] = dx;
+                acc[2].v[k].x += dx.x; acc[2].v[k].y += dx.y; acc[2].v[k].z += dx.z; acc[2].v[k].w += dx.w;
+            } else {
+                acc[2].v[k].x += o.v[k].x; acc[2].v[k].y += o.v[k].y; acc[2].v[k].z += o.v[k].z; acc[2].v[k].w += o.v[k].w;
+            }
         }
         store_row<VEC>(dz_out + r * C, lane, o);
     }
@@ -180,12 +239,12 @@ epilogue_ln_bwd(const float *__restrict__ dy, const float *__restrict__ z, const
     flush_column_sums<VEC, 3>(acc, outs, s_cols);
 }
 
-// out[c] += sum_r x[r][c]; with `mask_src` (the ReLU output) also dpre[r][c] = x[r][c] * (mask_src[r][c] > 0), summed.
+// out[c] += sum_r x[r][c]; with `mask_src` (the ReLU output) also dpre[r][c] = scale * x[r][c] * (mask_src[r][c] > 0), summed.
 // Any C that is a multiple of 4: a CTA's threads tile (rows x column chunks); out is zero-filled by the launcher.
 template <bool RELU>
 __global__ void __launch_bounds__(256)
 column_sum_kernel(const float *__restrict__ x, const float *__restrict__ mask_src, int64_t rows, int C, float *__restrict__ dpre,
-                  float *__restrict__ out) {
+                  float *__restrict__ out, float scale) {
     float4 *s_part = reinterpret_cast<float4 *>(msda_smem);          // [rows_per_pass][cols_per_pass]
     const int C4 = C >> 2;
     const int cols = C4 < 256 ? C4 : 256;                             // column chunks a CTA covers at a time
@@ -209,8 +268,9 @@ column_sum_kernel(const float *__restrict__ x, const float *__restrict__ mask_sr
                     const float4 *hs = reinterpret_cast<const float4 *>(mask_src) + r * C4 + c;
                     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                                  : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "l"(hs));
-                    v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f;
-                    v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+                    // `scale` = 1 / (1 - p) when h is the DROPPED ReLU output (h > 0 <=> positive and kept), else 1
+                    v.x = h.x > 0.f ? v.x * scale : 0.f; v.y = h.y > 0.f ? v.y * scale : 0.f;
+                    v.z = h.z > 0.f ? v.z * scale : 0.f; v.w = h.w > 0.f ? v.w * scale : 0.f;
                     reinterpret_cast<float4 *>(dpre)[r * C4 + c] = v;
                 }
                 return v;
@@ -240,5 +300,27 @@ column_sum_kernel(const float *__restrict__ x, const float *__restrict__ mask_sr
             if (r0 < r1) red_add_f32x4(out + 4 * c, acc);
         }
         __syncthreads();
+    }
+}
+
+// h *= keep / (1 - p) in place (dropout2, after the FFN's ReLU: deformable_transformer.py:244).  Because the result is
+// positive exactly where the ReLU output was positive AND kept, the backward needs no mask: relu_bwd with `scale`.
+__global__ void __launch_bounds__(256)
+dropout_inplace_kernel(float4 *__restrict__ h, int64_t n4, DropoutArgs da) {
+    const DropoutKey dk = dropout_key(da);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = h[i];
+        const float4 f = dropout_factor(dk, da, i);
+        v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
+        h[i] = v;
+    }
+}
+// the keep mask itself, one byte per element (tests: the kernels never materialise it)
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uchar4 *__restrict__ out, int64_t n4, DropoutArgs da) {
+    const DropoutKey dk = dropout_key(da);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 f = dropout_factor(dk, da, i);
+        out[i] = make_uchar4(f.x != 0.f, f.y != 0.f, f.z != 0.f, f.w != 0.f);
     }
 }

@@ -1227,26 +1227,40 @@ int msda_fused_backward_bf16(const uint16_t *go, const uint16_t *value, const in
 namespace {
 template <int VEC>
 int launch_ln_fwd(const float *x, const float *bias, const float *res, const float *gamma, const float *beta, float eps,
-                  int64_t rows, float *z, float *y, float *mean, float *rstd, cudaStream_t st) {
+                  int64_t rows, float *z, float *y, float *mean, float *rstd, const DropoutArgs *da, cudaStream_t st) {
     const int64_t want = (rows + 7) / 8;
     const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
-    epilogue_ln_fwd<VEC><<<grid, 256, 0, st>>>(x, bias, res, gamma, beta, eps, rows, z, y, mean, rstd);
+    if (da) epilogue_ln_fwd<VEC, true><<<grid, 256, 0, st>>>(x, bias, res, gamma, beta, eps, rows, z, y, mean, rstd, *da);
+    else epilogue_ln_fwd<VEC, false><<<grid, 256, 0, st>>>(x, bias, res, gamma, beta, eps, rows, z, y, mean, rstd, DropoutArgs{});
     return after_launch("epilogue_ln_fwd");
 }
 template <int VEC>
 int launch_ln_bwd(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma, int64_t rows,
-                  float *dz, float *dgamma, float *dbeta, float *dbias, cudaStream_t st) {
+                  float *dz, float *dgamma, float *dbeta, float *dbias, float *dx, const DropoutArgs *da, cudaStream_t st) {
     const int64_t want = (rows + 7) / 8;
     const int grid = (int)(want < (int64_t)sm_count() * 2 ? want : (int64_t)sm_count() * 2);
-    epilogue_ln_bwd<VEC><<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias);
+    if (da) epilogue_ln_bwd<VEC, true><<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, dx, *da);
+    else epilogue_ln_bwd<VEC, false><<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, nullptr, DropoutArgs{});
     return after_launch("epilogue_ln_bwd");
+}
+// p in [0, 1): keep <=> 32-bit word >= floor(p * 2^32)
+int make_dropout(const void *rng, uint32_t salt, float p, DropoutArgs *out, const char *who) {
+    if (!rng || misaligned(rng, 8)) return fail(MSDA_ERR_INVALID_ARGUMENT, "dropout: rng must point at two 8-byte aligned 64-bit words");
+    if (!(p >= 0.f && p < 1.f)) return fail(MSDA_ERR_INVALID_ARGUMENT, "dropout: p must be in [0, 1)");
+    (void)who;
+    out->rng = static_cast<const uint64_t *>(rng);
+    out->salt = salt;
+    out->thresh = (uint32_t)((double)p * 4294967296.0);
+    out->scale = 1.f / (1.f - p);
+    return MSDA_OK;
 }
 int zero_fill(float *p, int64_t n, cudaStream_t st, const char *what) {
     if (!p || n <= 0) return MSDA_OK;
     const cudaError_t e = cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, st);
     return e == cudaSuccess ? MSDA_OK : fail_cuda(e, what);
 }
-int column_sum_any(bool relu, const float *x, const float *h, int64_t rows, int C, float *dpre, float *out, cudaStream_t st) {
+int column_sum_any(bool relu, const float *x, const float *h, int64_t rows, int C, float *dpre, float *out, cudaStream_t st,
+                   float scale = 1.f) {
     if (rows < 0 || C <= 0 || (C & 3)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: channels must be a positive multiple of 4");
     if (!out) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_column_sum: null output");
     if (const int rc = zero_fill(out, C, st, "msda_column_sum: memset")) return rc;
@@ -1258,17 +1272,17 @@ int column_sum_any(bool relu, const float *x, const float *h, int64_t rows, int 
     const int64_t want = (rows + 31) / 32, cap = (int64_t)sm_count() * (relu ? 4 : 2);
     const int grid = (int)(want < cap ? want : cap);
     const size_t smem = 256 * sizeof(float4);
-    if (relu) column_sum_kernel<true><<<grid, 256, smem, st>>>(x, h, rows, C, dpre, out);
-    else column_sum_kernel<false><<<grid, 256, smem, st>>>(x, nullptr, rows, C, nullptr, out);
+    if (relu) column_sum_kernel<true><<<grid, 256, smem, st>>>(x, h, rows, C, dpre, out, scale);
+    else column_sum_kernel<false><<<grid, 256, smem, st>>>(x, nullptr, rows, C, nullptr, out, 1.f);
     return after_launch("column_sum_kernel");
 }
 }  // namespace
 
 extern "C" {
 
-int msda_epilogue_ln_forward_f32(const float *x, const float *bias, const float *residual, const float *gamma,
-                                 const float *beta, float eps, int64_t rows, int channels, float *z, float *y, float *mean,
-                                 float *rstd, msda_stream_t stream) {
+static int ln_forward_any(const float *x, const float *bias, const float *residual, const float *gamma, const float *beta, float eps,
+                          int64_t rows, int channels, const DropoutArgs *da, float *z, float *y, float *mean, float *rstd,
+                          msda_stream_t stream) {
     if (rows < 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_forward_f32: negative row count");
     if (rows == 0) return MSDA_OK;
     if (!x || !residual || !gamma || !beta || !z || !y || !mean || !rstd)
@@ -1278,17 +1292,17 @@ int msda_epilogue_ln_forward_f32(const float *x, const float *bias, const float 
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_forward_f32: pointers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     switch (channels) {
-        case 128: return launch_ln_fwd<1>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
-        case 256: return launch_ln_fwd<2>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
-        case 512: return launch_ln_fwd<4>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
-        case 1024: return launch_ln_fwd<8>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, st);
+        case 128: return launch_ln_fwd<1>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, da, st);
+        case 256: return launch_ln_fwd<2>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, da, st);
+        case 512: return launch_ln_fwd<4>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, da, st);
+        case 1024: return launch_ln_fwd<8>(x, bias, residual, gamma, beta, eps, rows, z, y, mean, rstd, da, st);
         default: return fail(MSDA_ERR_UNSUPPORTED, "msda_epilogue_ln_forward_f32: channels must be 128, 256, 512 or 1024");
     }
 }
 
-int msda_epilogue_ln_backward_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
-                                  int64_t rows, int channels, float *dz, float *dgamma, float *dbeta, float *dbias,
-                                  msda_stream_t stream) {
+static int ln_backward_any(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
+                           int64_t rows, int channels, const DropoutArgs *da, float *dz, float *dx, float *dgamma, float *dbeta,
+                           float *dbias, msda_stream_t stream) {
     if (rows < 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: negative row count");
     if (channels != 128 && channels != 256 && channels != 512 && channels != 1024)
         return fail(MSDA_ERR_UNSUPPORTED, "msda_epilogue_ln_backward_f32: channels must be 128, 256, 512 or 1024");
@@ -1298,16 +1312,72 @@ int msda_epilogue_ln_backward_f32(const float *dy, const float *z, const float *
     if (const int rc = zero_fill(dbeta, channels, st, "msda_epilogue_ln_backward_f32: memset")) return rc;
     if (const int rc = zero_fill(dbias, channels, st, "msda_epilogue_ln_backward_f32: memset")) return rc;
     if (rows == 0) return MSDA_OK;
-    if (!dy || !z || !mean || !rstd || !gamma || !dz) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: null pointer");
+    if (!dy || !z || !mean || !rstd || !gamma || !dz || (da && !dx))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: null pointer");
     if (misaligned(dy, 16) || misaligned(z, 16) || misaligned(gamma, 16) || misaligned(dz, 16) || misaligned(dgamma, 16) ||
-        misaligned(dbeta, 16) || (dbias && misaligned(dbias, 16)))
+        misaligned(dbeta, 16) || (dbias && misaligned(dbias, 16)) || (da && misaligned(dx, 16)))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_epilogue_ln_backward_f32: pointers must be 16-byte aligned");
     switch (channels) {
-        case 128: return launch_ln_bwd<1>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
-        case 256: return launch_ln_bwd<2>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
-        case 512: return launch_ln_bwd<4>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
-        default: return launch_ln_bwd<8>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, st);
+        case 128: return launch_ln_bwd<1>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, dx, da, st);
+        case 256: return launch_ln_bwd<2>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, dx, da, st);
+        case 512: return launch_ln_bwd<4>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, dx, da, st);
+        default: return launch_ln_bwd<8>(dy, z, mean, rstd, gamma, rows, dz, dgamma, dbeta, dbias, dx, da, st);
     }
+}
+
+int msda_epilogue_ln_forward_f32(const float *x, const float *bias, const float *residual, const float *gamma,
+                                 const float *beta, float eps, int64_t rows, int channels, float *z, float *y, float *mean,
+                                 float *rstd, msda_stream_t stream) {
+    return ln_forward_any(x, bias, residual, gamma, beta, eps, rows, channels, nullptr, z, y, mean, rstd, stream);
+}
+
+int msda_epilogue_ln_backward_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
+                                  int64_t rows, int channels, float *dz, float *dgamma, float *dbeta, float *dbias,
+                                  msda_stream_t stream) {
+    return ln_backward_any(dy, z, mean, rstd, gamma, rows, channels, nullptr, dz, nullptr, dgamma, dbeta, dbias, stream);
+}
+
+int msda_epilogue_ln_dropout_forward_f32(const float *x, const float *bias, const float *residual, const float *gamma,
+                                         const float *beta, float eps, int64_t rows, int channels, const void *rng,
+                                         uint32_t salt, float p, float *z, float *y, float *mean, float *rstd,
+                                         msda_stream_t stream) {
+    DropoutArgs da;
+    if (const int rc = make_dropout(rng, salt, p, &da, "msda_epilogue_ln_dropout_forward_f32")) return rc;
+    return ln_forward_any(x, bias, residual, gamma, beta, eps, rows, channels, &da, z, y, mean, rstd, stream);
+}
+
+int msda_epilogue_ln_dropout_backward_f32(const float *dy, const float *z, const float *mean, const float *rstd,
+                                          const float *gamma, int64_t rows, int channels, const void *rng, uint32_t salt,
+                                          float p, float *dz, float *dx, float *dgamma, float *dbeta, float *dbias,
+                                          msda_stream_t stream) {
+    DropoutArgs da;
+    if (const int rc = make_dropout(rng, salt, p, &da, "msda_epilogue_ln_dropout_backward_f32")) return rc;
+    return ln_backward_any(dy, z, mean, rstd, gamma, rows, channels, &da, dz, dx, dgamma, dbeta, dbias, stream);
+}
+
+static int dropout_stream_grid(int64_t n4) {
+    const int64_t want = (n4 + 255) / 256, cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+int msda_dropout_inplace_f32(float *h, int64_t n, const void *rng, uint32_t salt, float p, msda_stream_t stream) {
+    if (n < 0 || (n & 3)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_inplace_f32: element count must be a non-negative multiple of 4");
+    DropoutArgs da;
+    if (const int rc = make_dropout(rng, salt, p, &da, "msda_dropout_inplace_f32")) return rc;
+    if (n == 0) return MSDA_OK;
+    if (!h || misaligned(h, 16)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_inplace_f32: h must be a 16-byte aligned pointer");
+    dropout_inplace_kernel<<<dropout_stream_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(h), n / 4, da);
+    return after_launch("dropout_inplace_kernel");
+}
+
+int msda_dropout_mask_u8(const void *rng, uint32_t salt, float p, int64_t n, uint8_t *keep, msda_stream_t stream) {
+    if (n < 0 || (n & 3)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_mask_u8: element count must be a non-negative multiple of 4");
+    DropoutArgs da;
+    if (const int rc = make_dropout(rng, salt, p, &da, "msda_dropout_mask_u8")) return rc;
+    if (n == 0) return MSDA_OK;
+    if (!keep || misaligned(keep, 4)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_dropout_mask_u8: keep must be a 4-byte aligned pointer");
+    dropout_mask_kernel<<<dropout_stream_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uchar4 *>(keep), n / 4, da);
+    return after_launch("dropout_mask_kernel");
 }
 
 int msda_column_sum_f32(const float *x, int64_t rows, int channels, float *out, msda_stream_t stream) {
@@ -1317,6 +1387,12 @@ int msda_column_sum_f32(const float *x, int64_t rows, int channels, float *out, 
 int msda_relu_backward_column_sum_f32(const float *dh, const float *h, int64_t rows, int channels, float *dpre, float *dbias,
                                       msda_stream_t stream) {
     return column_sum_any(true, dh, h, rows, channels, dpre, dbias, (cudaStream_t)stream);
+}
+
+int msda_relu_dropout_backward_column_sum_f32(const float *dh, const float *h_dropped, float p, int64_t rows, int channels,
+                                              float *dpre, float *dbias, msda_stream_t stream) {
+    if (!(p >= 0.f && p < 1.f)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_relu_dropout_backward_column_sum_f32: p must be in [0, 1)");
+    return column_sum_any(true, dh, h_dropped, rows, channels, dpre, dbias, (cudaStream_t)stream, 1.f / (1.f - p));
 }
 
 }  // extern "C"

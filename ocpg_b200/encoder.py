@@ -12,7 +12,9 @@ Differences from the reference, all on the host side:
     materialising sampling_locations / attention_weights, which the encoder throws away (:251); it also runs the
     layer's epilogue -- bias + residual + LayerNorm after the attention and after the FFN, the FFN's bias + ReLU and
     every bias gradient -- through the streaming kernels of ocpg_b200/epilogue.py
-    whenever dropout is inactive (p == 0 or eval mode) and the activation is ReLU; otherwise the reference's graph;
+    whenever the activation is ReLU (otherwise the reference's graph).  In training mode with p > 0 the three dropouts
+    of the layer (:226-235) run inside those kernels from one pair of generator words per layer call
+    (``epilogue.new_rng``): same distribution as ``nn.Dropout``, a different mask stream;
   * the reference wraps the attention in ``autocast(enabled=False)`` (:250); so does this.
 """
 from __future__ import annotations
@@ -61,9 +63,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return self.norm2(src + self.dropout3(self.linear2(hidden)))
 
     def _epilogue_ok(self, src):
-        dropout_off = not self.training or max(self.dropout1.p, self.dropout2.p, self.dropout3.p) == 0.0
-        return (self.fused and dropout_off and self.activation_name == "relu" and src.shape[-1] in epilogue.LN_CHANNELS
-                and epilogue.supported(src, self.norm1.weight))
+        ps = (self.dropout1.p, self.dropout2.p, self.dropout3.p)
+        return (self.fused and all(0.0 <= p < 1.0 for p in ps) and self.activation_name == "relu"
+                and src.shape[-1] in epilogue.LN_CHANNELS and epilogue.supported(src, self.norm1.weight))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         if self._epilogue_ok(src):
@@ -71,11 +73,13 @@ class DeformableTransformerEncoderLayer(nn.Module):
                 core = self.self_attn.attend(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                                              level_start_index, padding_mask)[0]
             proj = self.self_attn.output_proj
+            p1, p2, p3 = ((self.dropout1.p, self.dropout2.p, self.dropout3.p) if self.training else (0.0, 0.0, 0.0))
+            rng = epilogue.new_rng(src.device) if max(p1, p2, p3) > 0.0 else None
             src = epilogue.bias_residual_layer_norm(F.linear(core, proj.weight), proj.bias, src, self.norm1.weight,
-                                                    self.norm1.bias, self.norm1.eps)             # :253-254
-            hidden = epilogue.linear_relu(src, self.linear1.weight, self.linear1.bias)           # :244
+                                                    self.norm1.bias, self.norm1.eps, rng, 1, p1)             # :253-254
+            hidden = epilogue.linear_relu(src, self.linear1.weight, self.linear1.bias, rng, 2, p2)           # :244
             return epilogue.bias_residual_layer_norm(F.linear(hidden, self.linear2.weight), self.linear2.bias, src,
-                                                     self.norm2.weight, self.norm2.bias, self.norm2.eps)   # :245-247
+                                                     self.norm2.weight, self.norm2.bias, self.norm2.eps, rng, 3, p3)   # :245-247
         with torch.autocast(device_type=src.device.type, enabled=False):
             attn_out = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                                       level_start_index, padding_mask)[0]

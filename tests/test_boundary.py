@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
         assert hasattr(L, s), s
-    assert ocpg_b200.lib().msda_abi_version() == 3
+    assert ocpg_b200.lib().msda_abi_version() == 4
 
 
 def test_library_is_sm100a_only():
