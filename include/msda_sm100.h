@@ -198,6 +198,24 @@ int msda_relu_dropout_backward_column_sum_f32(const float *dh, const float *h_dr
 
 int msda_dropout_mask_u8(const void *rng, uint32_t salt, float p, int64_t n, uint8_t *keep, msda_stream_t stream);
 
+/* ---- decoder-side consumers of the cross-attention's outputs (new; SURVEY.md section 8f rank 3;
+ *      DeformableTransformerDecoder.forward, models/deformable_transformer.py:353-375).
+ *        msda_decoder_select_samples_f32   per (frame, query): the `top` largest of the num_heads*num_levels*num_point
+ *            attention weights in descending order (ties: ascending index), and the sampling locations of those points
+ *            divided by their level's valid ratio -- `samples_keep` of :368-375 in one launch.
+ *            sampling_loc [batch][num_query][heads][levels][points][2], attn_weight [batch][num_query][heads][levels][points],
+ *            valid_ratios [batch][levels][2] (w, h); out: samples_keep [batch][num_query][top][2], top_weights
+ *            [batch][num_query][top] (may be NULL), top_idx int64 [batch][num_query][top] (may be NULL).
+ *            Needs top <= 32 and top <= heads*levels*points <= 256 (the reference: 30 of 128).
+ *        msda_decoder_reference_points_f32 reference_points_input [batch][num_query][levels][ref_dim] =
+ *            reference_points [batch][num_query][ref_dim] * valid_ratios (repeated twice for ref_dim == 4)   (:358-363) ---- */
+int msda_decoder_select_samples_f32(const float *sampling_loc, const float *attn_weight, const float *valid_ratios,
+                                    int batch, int num_query, int num_heads, int num_levels, int num_point, int top,
+                                    float *samples_keep, float *top_weights, int64_t *top_idx, msda_stream_t stream);
+
+int msda_decoder_reference_points_f32(const float *reference_points, const float *valid_ratios, int batch, int num_query,
+                                      int num_levels, int ref_dim, float *reference_points_input, msda_stream_t stream);
+
 /* Which kernel a call with these dimensions runs: 1 = the sm_100a tiled kernel (channels == 32,
  * num_levels <= 16, num_levels*num_point <= 32), 0 = the generic kernel (any shape).  For tests and
  * benchmarks; `elem_bytes` is 2, 4 or 8. */

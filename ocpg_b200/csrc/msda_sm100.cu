@@ -702,6 +702,7 @@ __global__ void msda_f32_to_bf16(const float4 *__restrict__ src, uint2 *__restri
 }
 
 #include "msda_epilogue.cuh"
+#include "msda_decoder.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Generic kernels: any D, L, P; float or double.  Correctness path for the shapes the tiled kernels
@@ -1393,6 +1394,53 @@ int msda_relu_dropout_backward_column_sum_f32(const float *dh, const float *h_dr
                                               float *dpre, float *dbias, msda_stream_t stream) {
     if (!(p >= 0.f && p < 1.f)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_relu_dropout_backward_column_sum_f32: p must be in [0, 1)");
     return column_sum_any(true, dh, h_dropped, rows, channels, dpre, dbias, (cudaStream_t)stream, 1.f / (1.f - p));
+}
+
+// ---- decoder-side consumers ----
+int msda_decoder_select_samples_f32(const float *sampling_loc, const float *attn_weight, const float *valid_ratios, int batch,
+                                    int num_query, int num_heads, int num_levels, int num_point, int top,
+                                    float *samples_keep, float *top_weights, int64_t *top_idx, msda_stream_t stream) {
+    if (batch < 0 || num_query < 0 || num_heads <= 0 || num_levels <= 0 || num_point <= 0 || top <= 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_select_samples_f32: non-positive dimension");
+    const int64_t K64 = (int64_t)num_heads * num_levels * num_point;
+    if (top > 32 || K64 > 256 || top > K64)
+        return fail(MSDA_ERR_UNSUPPORTED, "msda_decoder_select_samples_f32: needs top <= 32, top <= heads*levels*points <= 256");
+    const int64_t rows = (int64_t)batch * num_query;
+    if (rows == 0) return MSDA_OK;
+    if (!sampling_loc || !attn_weight || !valid_ratios || !samples_keep)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_select_samples_f32: null pointer");
+    if (misaligned(sampling_loc, 8) || misaligned(valid_ratios, 8) || misaligned(samples_keep, 8) || misaligned(attn_weight, 4) ||
+        (top_idx && misaligned(top_idx, 8)))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_select_samples_f32: misaligned pointer");
+    const int K = (int)K64;
+    const int grid = (int)((rows + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MSDA_SELECT(ITEMS) decoder_select_samples_kernel<ITEMS><<<grid, 128, 0, st>>>(sampling_loc, attn_weight, valid_ratios, rows, \
+        num_query, K, num_levels, num_point, top, samples_keep, top_weights, top_idx)
+    if (K <= 32) MSDA_SELECT(1);
+    else if (K <= 64) MSDA_SELECT(2);
+    else if (K <= 128) MSDA_SELECT(4);
+    else MSDA_SELECT(8);
+#undef MSDA_SELECT
+    return after_launch("decoder_select_samples_kernel");
+}
+
+int msda_decoder_reference_points_f32(const float *reference_points, const float *valid_ratios, int batch, int num_query,
+                                      int num_levels, int ref_dim, float *reference_points_input, msda_stream_t stream) {
+    if (batch < 0 || num_query < 0 || num_levels <= 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_reference_points_f32: non-positive dimension");
+    if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_reference_points_f32: ref_dim must be 2 or 4");
+    const int64_t total = (int64_t)batch * num_query * num_levels;
+    if (total == 0) return MSDA_OK;
+    if (!reference_points || !valid_ratios || !reference_points_input)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_reference_points_f32: null pointer");
+    const size_t al = ref_dim == 2 ? 8 : 16;
+    if (misaligned(reference_points, al) || misaligned(reference_points_input, al) || misaligned(valid_ratios, 8))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_decoder_reference_points_f32: misaligned pointer");
+    const int64_t want = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
+    decoder_reference_points_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        reference_points, valid_ratios, total, num_query, num_levels, ref_dim, reference_points_input);
+    return after_launch("decoder_reference_points_kernel");
 }
 
 }  // extern "C"
