@@ -216,6 +216,23 @@ int msda_decoder_select_samples_f32(const float *sampling_loc, const float *attn
 int msda_decoder_reference_points_f32(const float *reference_points, const float *valid_ratios, int batch, int num_query,
                                       int num_levels, int ref_dim, float *reference_points_input, msda_stream_t stream);
 
+/* ---- the layout traffic either side of the encoder (new; SURVEY.md section 8f rank 4;
+ *      DeformableTransformer.forward, models/deformable_transformer.py:149-169 and :205-212).
+ *        msda_flatten_levels_f32    src_flatten [batch][S][channels] = cat_l transpose(src_l [batch][channels][H_l*W_l]) and,
+ *            when pos_levels != NULL, pos_flatten = the same of pos_l + level_embed[l] (level_embed [levels][channels], may be
+ *            NULL); S = sum_l H_l*W_l.  `src_levels` / `pos_levels` / `heights` / `widths` are HOST arrays of num_levels
+ *            entries (device pointers, ints) -- the reference takes (h, w) from the maps' shapes on the host too (:151-153).
+ *        msda_unflatten_levels_f32  maps[l] [batch][channels][H_l*W_l] = rows [start_l, start_l + H_l*W_l) of
+ *            flat [batch][spatial_size][channels], for the FIRST num_levels levels (the reference converts all but the
+ *            last, :207); spatial_size >= sum of those levels' pixels (0 = exactly that sum).
+ *      Each is the other's backward.  num_levels <= 8; any channel count. ---- */
+int msda_flatten_levels_f32(int num_levels, const float *const *src_levels, const float *const *pos_levels,
+                            const float *level_embed, const int *heights, const int *widths, int batch, int channels,
+                            float *src_flatten, float *pos_flatten, msda_stream_t stream);
+
+int msda_unflatten_levels_f32(int num_levels, const float *flat, const int *heights, const int *widths, int batch,
+                              int channels, int spatial_size, float *const *maps, msda_stream_t stream);
+
 /* Which kernel a call with these dimensions runs: 1 = the sm_100a tiled kernel (channels == 32,
  * num_levels <= 16, num_levels*num_point <= 32), 0 = the generic kernel (any shape).  For tests and
  * benchmarks; `elem_bytes` is 2, 4 or 8. */

@@ -29,7 +29,8 @@ SYMBOLS = [
     "msda_fused_backward_bf16", "msda_epilogue_ln_forward_f32", "msda_epilogue_ln_backward_f32", "msda_column_sum_f32",
     "msda_relu_backward_column_sum_f32", "msda_epilogue_ln_dropout_forward_f32", "msda_epilogue_ln_dropout_backward_f32",
     "msda_dropout_inplace_f32", "msda_relu_dropout_backward_column_sum_f32", "msda_dropout_mask_u8",
-    "msda_decoder_select_samples_f32", "msda_decoder_reference_points_f32",
+    "msda_decoder_select_samples_f32", "msda_decoder_reference_points_f32", "msda_flatten_levels_f32",
+    "msda_unflatten_levels_f32",
 ]
 
 _lib = None
@@ -46,6 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/msda_sm100.cu for sm_100a into ocpg_b200/lib/libmsda_sm100.so (cross-compiles
     without a GPU).  Rebuilds when the source or header is newer than the library."""
     deps = [SRC, os.path.join(_PKG, "csrc", "msda_epilogue.cuh"), os.path.join(_PKG, "csrc", "msda_decoder.cuh"),
+            os.path.join(_PKG, "csrc", "msda_flatten.cuh"),
             os.path.join(INCLUDE, "msda_sm100.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
@@ -126,6 +128,10 @@ def lib() -> ctypes.CDLL:
     L.msda_decoder_select_samples_f32.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p] * 3 + [c_void_p]
     L.msda_decoder_reference_points_f32.restype = c_int
     L.msda_decoder_reference_points_f32.argtypes = [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]
+    L.msda_flatten_levels_f32.restype = c_int
+    L.msda_flatten_levels_f32.argtypes = [c_int] + [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 3
+    L.msda_unflatten_levels_f32.restype = c_int
+    L.msda_unflatten_levels_f32.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     if L.msda_abi_version() != 4:
         raise RuntimeError("libmsda_sm100.so ABI version mismatch")
     _lib = L

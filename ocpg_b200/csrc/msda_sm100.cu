@@ -703,6 +703,7 @@ __global__ void msda_f32_to_bf16(const float4 *__restrict__ src, uint2 *__restri
 
 #include "msda_epilogue.cuh"
 #include "msda_decoder.cuh"
+#include "msda_flatten.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Generic kernels: any D, L, P; float or double.  Correctness path for the shapes the tiled kernels
@@ -1441,6 +1442,74 @@ int msda_decoder_reference_points_f32(const float *reference_points, const float
     decoder_reference_points_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
         reference_points, valid_ratios, total, num_query, num_levels, ref_dim, reference_points_input);
     return after_launch("decoder_reference_points_kernel");
+}
+
+// ---- caller-side flattening ----
+static int flatten_setup(FlattenArgs &a, const char *who, int num_levels, const int *heights, const int *widths, int batch,
+                         int channels, int spatial_size) {
+    if (num_levels <= 0 || num_levels > kFlatMaxLevels) return fail(MSDA_ERR_UNSUPPORTED, "flatten: 1 <= num_levels <= 8");
+    if (batch < 0 || channels <= 0 || !heights || !widths) return fail(MSDA_ERR_INVALID_ARGUMENT, "flatten: bad dimension / null shape array");
+    (void)who;
+    memset(&a, 0, sizeof(a));
+    a.L = num_levels; a.N = batch; a.C = channels;
+    a.tiles_c = (channels + 31) / 32;
+    int64_t rows = 0, tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        if (heights[l] <= 0 || widths[l] <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "flatten: non-positive level shape");
+        const int64_t hw = (int64_t)heights[l] * widths[l];
+        if (rows + hw > INT32_MAX / 2) return fail(MSDA_ERR_UNSUPPORTED, "flatten: more than 2^30 pixels per frame");
+        a.lv[l].hw = (int)hw;
+        a.lv[l].start = (int)rows;
+        a.lv[l].tiles_hw = (int)((hw + 31) / 32);
+        a.lv[l].tile_begin = (int)tiles;
+        tiles += (int64_t)a.lv[l].tiles_hw * a.tiles_c;
+        rows += hw;
+    }
+    if (tiles > INT32_MAX) return fail(MSDA_ERR_UNSUPPORTED, "flatten: too many tiles per frame");
+    a.tiles_per_frame = (int)tiles;
+    a.S = spatial_size > 0 ? spatial_size : (int)rows;
+    if (a.S < rows) return fail(MSDA_ERR_INVALID_ARGUMENT, "flatten: spatial_size smaller than the levels' pixels");
+    return MSDA_OK;
+}
+static int flatten_grid(const FlattenArgs &a) {
+    const int64_t total = (int64_t)a.N * a.tiles_per_frame, cap = (int64_t)sm_count() * 8;
+    return (int)(total < cap ? total : cap);
+}
+
+int msda_flatten_levels_f32(int num_levels, const float *const *src_levels, const float *const *pos_levels,
+                            const float *level_embed, const int *heights, const int *widths, int batch, int channels,
+                            float *src_flatten, float *pos_flatten, msda_stream_t stream) {
+    FlattenArgs a;
+    if (const int rc = flatten_setup(a, "msda_flatten_levels_f32", num_levels, heights, widths, batch, channels, 0)) return rc;
+    if (batch == 0) return MSDA_OK;
+    if (!src_levels || !src_flatten || (pos_levels && !pos_flatten)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_flatten_levels_f32: null pointer");
+    for (int l = 0; l < num_levels; ++l) {
+        if (!src_levels[l] || (pos_levels && !pos_levels[l])) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_flatten_levels_f32: null level pointer");
+        a.lv[l].src = src_levels[l];
+        a.lv[l].pos = pos_levels ? pos_levels[l] : nullptr;
+    }
+    a.level_embed = level_embed;
+    a.src_flat = src_flatten;
+    a.pos_flat = pos_flatten;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos_levels) flatten_levels_kernel<true><<<flatten_grid(a), 256, 0, st>>>(a);
+    else flatten_levels_kernel<false><<<flatten_grid(a), 256, 0, st>>>(a);
+    return after_launch("flatten_levels_kernel");
+}
+
+int msda_unflatten_levels_f32(int num_levels, const float *flat, const int *heights, const int *widths, int batch, int channels,
+                              int spatial_size, float *const *maps, msda_stream_t stream) {
+    FlattenArgs a;
+    if (const int rc = flatten_setup(a, "msda_unflatten_levels_f32", num_levels, heights, widths, batch, channels, spatial_size)) return rc;
+    if (batch == 0) return MSDA_OK;
+    if (!flat || !maps) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_unflatten_levels_f32: null pointer");
+    for (int l = 0; l < num_levels; ++l) {
+        if (!maps[l]) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_unflatten_levels_f32: null level pointer");
+        a.lv[l].map_out = maps[l];
+    }
+    a.flat_in = flat;
+    unflatten_levels_kernel<<<flatten_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
+    return after_launch("unflatten_levels_kernel");
 }
 
 }  // extern "C"
