@@ -1444,15 +1444,40 @@ int msda_decoder_reference_points_f32(const float *reference_points, const float
     return after_launch("decoder_reference_points_kernel");
 }
 
+}  // extern "C"
+
+namespace {
+template <typename K>
+int flatten_launch(const FlattenArgs &a, K kernel, size_t smem, cudaStream_t st, const char *what) {
+    // > 48 KB of dynamic shared memory needs the opt-in; set on every call (cheap, and correct on every device)
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(e, "flatten: cudaFuncSetAttribute");
+    }
+    int per_sm = 0;                  // resident CTAs per SM of this kernel: one full wave of persistent CTAs
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm <= 0) per_sm = 1;
+    const int64_t total = (int64_t)a.N * a.tiles_per_frame, cap = (int64_t)sm_count() * per_sm;
+    kernel<<<(int)(total < cap ? total : cap), 256, smem, st>>>(a);
+    return after_launch(what);
+}
+}  // namespace
+
+extern "C" {
+
 // ---- caller-side flattening ----
 static int flatten_setup(FlattenArgs &a, const char *who, int num_levels, const int *heights, const int *widths, int batch,
-                         int channels, int spatial_size) {
+                         int channels, int spatial_size, bool *vec4) {
     if (num_levels <= 0 || num_levels > kFlatMaxLevels) return fail(MSDA_ERR_UNSUPPORTED, "flatten: 1 <= num_levels <= 8");
     if (batch < 0 || channels <= 0 || !heights || !widths) return fail(MSDA_ERR_INVALID_ARGUMENT, "flatten: bad dimension / null shape array");
     (void)who;
     memset(&a, 0, sizeof(a));
     a.L = num_levels; a.N = batch; a.C = channels;
-    a.tiles_c = (channels + 31) / 32;
+    // 16-byte kernels when every level's pixel count and the channel count are multiples of 4 (pointers: checked by the caller)
+    bool v4 = channels % 4 == 0;
+    for (int l = 0; l < num_levels; ++l) v4 = v4 && ((int64_t)heights[l] * widths[l]) % 4 == 0;
+    *vec4 = v4;
+    const int tile_hw = v4 ? kV4Tile : kFlatTileHW, tile_c = v4 ? kV4Tile : kFlatTileC;
+    a.tiles_c = (channels + tile_c - 1) / tile_c;
     int64_t rows = 0, tiles = 0;
     for (int l = 0; l < num_levels; ++l) {
         if (heights[l] <= 0 || widths[l] <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "flatten: non-positive level shape");
@@ -1460,7 +1485,7 @@ static int flatten_setup(FlattenArgs &a, const char *who, int num_levels, const 
         if (rows + hw > INT32_MAX / 2) return fail(MSDA_ERR_UNSUPPORTED, "flatten: more than 2^30 pixels per frame");
         a.lv[l].hw = (int)hw;
         a.lv[l].start = (int)rows;
-        a.lv[l].tiles_hw = (int)((hw + 31) / 32);
+        a.lv[l].tiles_hw = (int)((hw + tile_hw - 1) / tile_hw);
         a.lv[l].tile_begin = (int)tiles;
         tiles += (int64_t)a.lv[l].tiles_hw * a.tiles_c;
         rows += hw;
@@ -1471,20 +1496,23 @@ static int flatten_setup(FlattenArgs &a, const char *who, int num_levels, const 
     if (a.S < rows) return fail(MSDA_ERR_INVALID_ARGUMENT, "flatten: spatial_size smaller than the levels' pixels");
     return MSDA_OK;
 }
-static int flatten_grid(const FlattenArgs &a) {
-    const int64_t total = (int64_t)a.N * a.tiles_per_frame, cap = (int64_t)sm_count() * 8;
-    return (int)(total < cap ? total : cap);
-}
-
 int msda_flatten_levels_f32(int num_levels, const float *const *src_levels, const float *const *pos_levels,
                             const float *level_embed, const int *heights, const int *widths, int batch, int channels,
                             float *src_flatten, float *pos_flatten, msda_stream_t stream) {
     FlattenArgs a;
-    if (const int rc = flatten_setup(a, "msda_flatten_levels_f32", num_levels, heights, widths, batch, channels, 0)) return rc;
+    bool v4 = false;
+    if (const int rc = flatten_setup(a, "msda_flatten_levels_f32", num_levels, heights, widths, batch, channels, 0, &v4)) return rc;
     if (batch == 0) return MSDA_OK;
     if (!src_levels || !src_flatten || (pos_levels && !pos_flatten)) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_flatten_levels_f32: null pointer");
+    bool aligned = !misaligned(src_flatten, 16) && !(pos_flatten && misaligned(pos_flatten, 16)) && !(level_embed && misaligned(level_embed, 16));
     for (int l = 0; l < num_levels; ++l) {
         if (!src_levels[l] || (pos_levels && !pos_levels[l])) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_flatten_levels_f32: null level pointer");
+        aligned = aligned && !misaligned(src_levels[l], 16) && !(pos_levels && misaligned(pos_levels[l], 16));
+    }
+    if (v4 && !aligned) {
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_flatten_levels_f32: pointers must be 16-byte aligned when every H*W and channels are multiples of 4");
+    }
+    for (int l = 0; l < num_levels; ++l) {
         a.lv[l].src = src_levels[l];
         a.lv[l].pos = pos_levels ? pos_levels[l] : nullptr;
     }
@@ -1492,24 +1520,34 @@ int msda_flatten_levels_f32(int num_levels, const float *const *src_levels, cons
     a.src_flat = src_flatten;
     a.pos_flat = pos_flatten;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pos_levels) flatten_levels_kernel<true><<<flatten_grid(a), 256, 0, st>>>(a);
-    else flatten_levels_kernel<false><<<flatten_grid(a), 256, 0, st>>>(a);
-    return after_launch("flatten_levels_kernel");
+    if (v4) {
+        if (pos_levels) return flatten_launch(a, flatten_levels_v4_kernel<true>, 0, st, "flatten_levels_v4_kernel");
+        return flatten_launch(a, flatten_levels_v4_kernel<false>, 0, st, "flatten_levels_v4_kernel");
+    }
+    const size_t tile = sizeof(float) * kFlatTileC * (kFlatTileHW + 1) * kFlatStages;
+    if (pos_levels) return flatten_launch(a, flatten_levels_kernel<true>, 2 * tile, st, "flatten_levels_kernel");
+    return flatten_launch(a, flatten_levels_kernel<false>, tile, st, "flatten_levels_kernel");
 }
 
 int msda_unflatten_levels_f32(int num_levels, const float *flat, const int *heights, const int *widths, int batch, int channels,
                               int spatial_size, float *const *maps, msda_stream_t stream) {
     FlattenArgs a;
-    if (const int rc = flatten_setup(a, "msda_unflatten_levels_f32", num_levels, heights, widths, batch, channels, spatial_size)) return rc;
+    bool v4 = false;
+    if (const int rc = flatten_setup(a, "msda_unflatten_levels_f32", num_levels, heights, widths, batch, channels, spatial_size, &v4)) return rc;
     if (batch == 0) return MSDA_OK;
     if (!flat || !maps) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_unflatten_levels_f32: null pointer");
+    bool aligned = !misaligned(flat, 16);
     for (int l = 0; l < num_levels; ++l) {
         if (!maps[l]) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_unflatten_levels_f32: null level pointer");
+        aligned = aligned && !misaligned(maps[l], 16);
         a.lv[l].map_out = maps[l];
     }
+    if (v4 && !aligned)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_unflatten_levels_f32: pointers must be 16-byte aligned when every H*W and channels are multiples of 4");
     a.flat_in = flat;
-    unflatten_levels_kernel<<<flatten_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
-    return after_launch("unflatten_levels_kernel");
+    if (v4) return flatten_launch(a, unflatten_levels_v4_kernel, 0, (cudaStream_t)stream, "unflatten_levels_v4_kernel");
+    return flatten_launch(a, unflatten_levels_kernel, sizeof(float) * kFlatTileHW * (kFlatTileC + 1) * kFlatStages,
+                          (cudaStream_t)stream, "unflatten_levels_kernel");
 }
 
 }  // extern "C"

@@ -33,6 +33,12 @@ def _native_ok(tensors: Sequence[torch.Tensor]) -> bool:
             and all(t is not None and t.is_cuda and t.dtype == torch.float32 for t in tensors))
 
 
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """contiguous and 16-byte aligned (a view at an odd storage offset is copied)."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
@@ -45,11 +51,11 @@ def _flatten_native(srcs, poss, level_embed):
     N, C = srcs[0].shape[:2]
     hs, ws = [t.shape[2] for t in srcs], [t.shape[3] for t in srcs]
     S = sum(h * w for h, w in zip(hs, ws))
-    srcs = [t.contiguous() for t in srcs]
+    srcs = [_aligned(t) for t in srcs]
     src_flat = torch.empty(N, S, C, dtype=torch.float32, device=srcs[0].device)
     pos_flat = None
     if poss is not None:
-        poss = [t.contiguous() for t in poss]
+        poss = [_aligned(t) for t in poss]
         pos_flat = torch.empty_like(src_flat)
     with torch.cuda.device(src_flat.device):
         rc = _lib.lib().msda_flatten_levels_f32(
@@ -62,7 +68,7 @@ def _flatten_native(srcs, poss, level_embed):
 
 def _unflatten_native(flat, shapes):
     N, S, C = flat.shape
-    flat = flat.contiguous()
+    flat = _aligned(flat)
     maps = [torch.empty(N, C, h, w, dtype=torch.float32, device=flat.device) for h, w in shapes]
     with torch.cuda.device(flat.device):
         rc = _lib.lib().msda_unflatten_levels_f32(len(shapes), flat.data_ptr(), _int_array([h for h, _ in shapes]),
@@ -77,7 +83,7 @@ class _FlattenLevels(Function):
     @staticmethod
     def forward(ctx, L, has_pos, level_embed, *maps):
         srcs, poss = list(maps[:L]), (list(maps[L:]) if has_pos else None)
-        le = None if level_embed is None else level_embed.contiguous()
+        le = None if level_embed is None else _aligned(level_embed)
         src_flat, pos_flat = _flatten_native(srcs, poss, le)
         ctx.L, ctx.has_pos, ctx.has_le = L, has_pos, level_embed is not None
         ctx.shapes = [tuple(t.shape[2:]) for t in srcs]

@@ -60,6 +60,9 @@ def dev():
     ([(1, 1)], 1, 1),
     ([(33, 31), (2, 65)], 3, 40),
     ([(9, 9)] * 8, 2, 64),                                      # the maximum level count
+    ([(4, 5), (2, 2)], 2, 12),                                  # 16-byte kernels, partial tiles both ways
+    ([(10, 18), (8, 9), (4, 17)], 1, 72),                       # 16-byte kernels, C = 64 + 8
+    ([(80, 144), (40, 72), (20, 36), (10, 18)], 2, 256),        # configs[2] geometry
 ])
 def test_flatten_unflatten_bit_exact_with_grads(dev, levels, N, C):
     import ocpg_b200

@@ -49,7 +49,8 @@ def report(name, rows, C, nbytes, us, us_torch):
     print(json.dumps(rec), flush=True)
 
 
-for rows in (24100, 153000):
+ONLY = set(sys.argv[1:])            # e.g. `bench_epilogue.py layout` runs the flatten / decoder-consumer rows alone
+for rows in (() if ONLY and "epilogue" not in ONLY else (24100, 153000)):
     C = 256
     nset = max(2, int(400e6 // (rows * C * 4 * 4)) + 1)
     sets = [dict(x=torch.randn(rows, C, device=dev), r=torch.randn(rows, C, device=dev), dy=torch.randn(rows, C, device=dev)) for _ in range(nset)]
@@ -83,7 +84,7 @@ for rows in (24100, 153000):
     del sets, dpre
 
 # ---- dropout variants (training) ----
-for rows in (24100, 153000):
+for rows in (() if ONLY and "dropout" not in ONLY else (24100, 153000)):
     C = 256
     nset = max(2, int(400e6 // (rows * C * 4 * 4)) + 1)
     sets = [dict(x=torch.randn(rows, C, device=dev), r=torch.randn(rows, C, device=dev), dy=torch.randn(rows, C, device=dev)) for _ in range(nset)]
@@ -134,10 +135,10 @@ for wl in (A2D_ENCODER, YTVOS_ENCODER):
             out.append(s["mem"][:, at:at + h * w, :].reshape(N, h, w, C).permute(0, 3, 1, 2).contiguous())
             at += h * w
         return out
-    report(f"flatten_levels[{wl.name}]", N * S, C, N * S * C * 4 * 4, timeit([lambda s=s: flat_mod.flatten_levels(s["src"], s["pos"], le) for s in sets]),
+    report(f"flatten_levels[{wl.name}]", N * S, C, N * S * C * 4 * 4, timeit([lambda s=s: flat_mod._flatten_native(s["src"], s["pos"], le) for s in sets]),
            timeit([lambda s=s: torch_flatten(s) for s in sets]))
     cov = sum(h * w for h, w in wl.levels[:-1])
-    report(f"unflatten_levels[{wl.name}]", N * cov, C, N * cov * C * 4 * 2, timeit([lambda s=s: flat_mod.unflatten_levels(s["mem"], wl.levels[:-1]) for s in sets]),
+    report(f"unflatten_levels[{wl.name}]", N * cov, C, N * cov * C * 4 * 2, timeit([lambda s=s: flat_mod._unflatten_native(s["mem"], wl.levels[:-1]) for s in sets]),
            timeit([lambda s=s: torch_unflatten(s) for s in sets]))
     del sets
 N, Lq, M, Lv, P = 5, 5, 8, 4, 4
