@@ -87,6 +87,24 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return self.forward_ffn(src)
 
 
+_HOST_SHAPES = {}      # (data_ptr, version, device) of a spatial_shapes tensor -> its rows as Python ints
+
+
+def _shapes_on_host(spatial_shapes):
+    """``spatial_shapes`` as a list of (H, W) ints.  The reference iterates the CUDA tensor (one device->host copy per
+    call, deformable_transformer.py:269); here the copy happens once per tensor (identity + version), which also keeps the
+    forward free of synchronisation so that a whole training step can be captured into a CUDA graph."""
+    if not isinstance(spatial_shapes, torch.Tensor):
+        return [tuple(int(v) for v in hw) for hw in spatial_shapes]
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, str(spatial_shapes.device), tuple(spatial_shapes.shape))
+    hit = _HOST_SHAPES.get(key)
+    if hit is None:
+        if len(_HOST_SHAPES) > 64:
+            _HOST_SHAPES.clear()
+        hit = _HOST_SHAPES[key] = [tuple(hw) for hw in spatial_shapes.tolist()]
+    return hit
+
+
 class DeformableTransformerEncoder(nn.Module):
     def __init__(self, encoder_layer, num_layers):
         super().__init__()
@@ -99,7 +117,7 @@ class DeformableTransformerEncoder(nn.Module):
         re-scaled to every level's valid ratio (:268-281).  ``spatial_shapes`` is iterated on the host, as in
         the reference (one small device->host copy per call)."""
         per_level = []
-        shapes = spatial_shapes.tolist() if isinstance(spatial_shapes, torch.Tensor) else list(spatial_shapes)
+        shapes = _shapes_on_host(spatial_shapes)
         for lvl, (h, w) in enumerate(shapes):
             ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
             xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)

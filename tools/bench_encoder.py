@@ -43,6 +43,9 @@ def parse_args(argv=None):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-op-timing", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture the whole step (all micro-batches, forward + backward) in ONE "
+                    "CUDA graph and replay it: no host launch latency.  Single GPU (the all-reduce hooks stay eager)")
+    ap.add_argument("--dropout", type=float, default=0.0, help="dropout probability of the layers (reference training: 0.1)")
     return ap.parse_args(argv)
 
 
@@ -70,7 +73,8 @@ def main(argv=None):
     torch.backends.cudnn.allow_tf32 = args.gemm == "tf32"
 
     torch.manual_seed(0)                                     # replicated weights: same seed on every rank
-    enc = build_encoder(num_layers=args.layers, d_ffn=args.d_ffn, dropout=0.0, fused=not args.unfused).to(dev)
+    enc = build_encoder(num_layers=args.layers, d_ffn=args.d_ffn, dropout=args.dropout, fused=not args.unfused).to(dev)
+    enc.train()
     with torch.no_grad():                                    # offsets / logits that depend on the query, init-like spread
         for layer in enc.layers:
             layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
@@ -100,6 +104,29 @@ def main(argv=None):
         return reducer.finish()
 
     n0 = ocpg_b200.launch_count()
+    eager_step, launches_per_step = step, None
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph: single GPU only")
+        args.no_op_timing = True                 # CUDA events around library calls cannot be captured
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up off the default stream (allocator, cuBLAS handles, shape caches)
+            for _ in range(3):
+                eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in enc.parameters():
+            p.grad = None
+        c0 = ocpg_b200.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            eager_step()
+        launches_per_step = ocpg_b200.launch_count() - c0
+
+        def step():
+            graph.replay()
+            return 0
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -117,7 +144,7 @@ def main(argv=None):
     torch.cuda.synchronize()
     D.barrier()
     torch.cuda.synchronize()
-    launches = ocpg_b200.launch_count() - n1
+    launches = ocpg_b200.launch_count() - n1 if launches_per_step is None else launches_per_step * args.steps
     ms = D.max_over_ranks(e0.elapsed_time(e1) / args.steps, device=dev)
     op = {} if args.no_op_timing else MSDA.stop_timing()
     mem_gb = torch.cuda.max_memory_allocated(dev) / 2**30
@@ -131,7 +158,8 @@ def main(argv=None):
             "config": {"workload": wl.name, "layers": args.layers, "d_ffn": args.d_ffn, "frames_per_gpu": frames,
                        "micro_batch_frames": micro, "levels": [list(x) for x in wl.levels], "S": S,
                        "module": "reference graph (unfused)" if args.unfused else "fused softmax/locations, no emitted locations",
-                       "gemm_policy": args.gemm, "parallelism": f"frames sharded over {world} GPU(s); NCCL all-reduce of "
+                       "gemm_policy": args.gemm, "dropout": args.dropout,
+                       "launch": "one CUDA graph per step" if args.graph else "eager", "parallelism": f"frames sharded over {world} GPU(s); NCCL all-reduce of "
                        f"{n_params} weight gradients, one bucket per layer, overlapped with backward"},
             "allreduce_bytes_per_step": comm_bytes, "gpu_launches": launches, "peak_mem_gb": round(mem_gb, 2),
         }
