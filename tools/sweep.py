@@ -18,13 +18,14 @@ ap.add_argument("--dtype", default="f32")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--variants", default="default:")
 ap.add_argument("--ops", default="fwd,bwd")
+ap.add_argument("--sigma", type=float, default=2.0, help="init regime: std of the sampling offsets in pixels")
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
 args = ap.parse_args()
 wl = {"a2d": A2D_ENCODER, "ytvos": YTVOS_ENCODER, "decoder": A2D_DECODER}[args.workload]
 dev = torch.device("cuda:0")
 vdt = torch.bfloat16 if args.dtype == "bf16" else None
 nsets = 2 if wl is YTVOS_ENCODER else 4
-sets = [make_inputs(wl, args.regime, seed=i, device=dev, value_dtype=vdt) for i in range(nsets)]
+sets = [make_inputs(wl, args.regime, seed=i, device=dev, value_dtype=vdt, sigma_px=args.sigma) for i in range(nsets)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 vb = 2 if vdt is not None else 4
 fb, bb = wl.algorithmic_bytes(vb, vb)
@@ -49,7 +50,7 @@ for var in args.variants.split(";"):
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) * 1e3)
         med = statistics.median(ts)
-        rec = dict(workload=wl.name, regime=args.regime, dtype=args.dtype, variant=name, opts=opts, op=op, us_median=round(med, 2),
+        rec = dict(workload=wl.name, regime=args.regime, sigma_px=args.sigma, dtype=args.dtype, variant=name, opts=opts, op=op, us_median=round(med, 2),
                    us_min=round(min(ts), 2), gbs=round(nbytes / med / 1e3, 1), frac_of_6551=round(nbytes / med / 1e3 / 6551, 4))
         fout.write(json.dumps(rec) + "\n"); fout.flush()
         print("%-34s %-8s %-5s %-28s %-4s med %8.1f us  min %8.1f us  frac %.3f" % (wl.name, args.regime, args.dtype, name, op, med, min(ts), rec["frac_of_6551"]), flush=True)
