@@ -73,7 +73,7 @@ def _dtype_suffix(value, sampling_loc, attn_weight):
 
 
 def _stream(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream                        # cu:65: current stream
+    return _lib.raw_stream(device)                                               # cu:65: current stream
 
 
 # Optional device timing of the library calls inside a larger program (bench: the operator's share of an
@@ -125,7 +125,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     if int(im2col_step) <= 0:
         raise RuntimeError("im2col_step must be positive")
     sfx = _dtype_suffix(value, sampling_loc, attn_weight)
-    with torch.cuda.device(value.device), _Timed("forward", value.device):
+    with _lib.on_device(value.device), _Timed("forward", value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)   # fully overwritten
         rc = getattr(_lib.lib(), f"msda_forward_{sfx}")(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
@@ -145,7 +145,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
         raise RuntimeError("grad_output must have value's dtype and N*Lq*M*D elements")
     sfx = _dtype_suffix(value, sampling_loc, attn_weight)
-    with torch.cuda.device(value.device), _Timed("backward", value.device):
+    with _lib.on_device(value.device), _Timed("backward", value.device):
         grad_loc = torch.empty_like(sampling_loc)      # every element is written by the kernel
         grad_attn = torch.empty_like(attn_weight)
         st = _stream(value.device)
@@ -206,7 +206,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, offse
     sfx = {torch.float32: "f32", torch.bfloat16: "bf16"}.get(value.dtype)
     if sfx is None:
         raise RuntimeError(f"fused path: unsupported value dtype {value.dtype}")
-    with torch.cuda.device(value.device), _Timed("forward", value.device):
+    with _lib.on_device(value.device), _Timed("forward", value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         loc = torch.empty_like(offsets) if emit else None
         attn = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device) if emit else None
@@ -231,7 +231,7 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, offs
     sfx = {torch.float32: "f32", torch.bfloat16: "bf16"}.get(value.dtype)
     if sfx is None:
         raise RuntimeError(f"fused path: unsupported value dtype {value.dtype}")
-    with torch.cuda.device(value.device), _Timed("backward", value.device):
+    with _lib.on_device(value.device), _Timed("backward", value.device):
         g_off = torch.empty_like(offsets)
         g_logits = torch.empty_like(logits)
         g_loc = torch.empty_like(offsets) if need_grad_loc else None

@@ -32,7 +32,7 @@ TOP_SAMPLES = 30          # the reference's hard-coded "hyperpara 30" (:371-372)
 
 
 def _stream(t) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    return _lib.raw_stream(t.device)
 
 
 def _native_ok(*tensors) -> bool:
@@ -46,7 +46,7 @@ class _ScaleReferencePoints(Function):
         L = valid_ratios.shape[1]
         ref, vr = reference_points.contiguous(), valid_ratios.contiguous()
         out = torch.empty(N, Lq, L, rd, dtype=torch.float32, device=ref.device)
-        with torch.cuda.device(ref.device):
+        with _lib.on_device(ref.device):
             rc = _lib.lib().msda_decoder_reference_points_f32(ref.data_ptr(), vr.data_ptr(), N, Lq, L, rd, out.data_ptr(), _stream(ref))
         _lib.check(rc, "msda_decoder_reference_points_f32")
         ctx.save_for_backward(vr)
@@ -78,7 +78,7 @@ class _SelectTopSamples(Function):
         keep = torch.empty(N, Lq, top, 2, dtype=torch.float32, device=loc.device)
         weights = torch.empty(N, Lq, top, dtype=torch.float32, device=loc.device)
         idx = torch.empty(N, Lq, top, dtype=torch.int64, device=loc.device)
-        with torch.cuda.device(loc.device):
+        with _lib.on_device(loc.device):
             rc = _lib.lib().msda_decoder_select_samples_f32(loc.data_ptr(), aw.data_ptr(), vr.data_ptr(), N, Lq, M, L, P, int(top),
                                                             keep.data_ptr(), weights.data_ptr(), idx.data_ptr(), _stream(loc))
         _lib.check(rc, "msda_decoder_select_samples_f32")

@@ -105,6 +105,31 @@ def _shapes_on_host(spatial_shapes):
     return hit
 
 
+_PIXEL_CENTRES = {}
+
+
+def _pixel_centres(spatial_shapes, device):
+    """Per flattened query: pixel-centre coordinates (x + 0.5, y + 0.5), its level's (W, H) as float32 and its level index.
+    Built like the reference (linspace(0.5, size - 0.5, size) + meshgrid, :271-272), cached per shapes tensor and device."""
+    shapes = _shapes_on_host(spatial_shapes)
+    key = (tuple(shapes), str(device))
+    hit = _PIXEL_CENTRES.get(key)
+    if hit is None:
+        gx, gy, sw, sh, lv = [], [], [], [], []
+        for lvl, (h, w) in enumerate(shapes):
+            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
+            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)
+            my, mx = torch.meshgrid(ys, xs, indexing="ij")
+            gx.append(mx.reshape(-1)); gy.append(my.reshape(-1))
+            sw.append(torch.full((h * w,), float(w), dtype=torch.float32, device=device))
+            sh.append(torch.full((h * w,), float(h), dtype=torch.float32, device=device))
+            lv.append(torch.full((h * w,), lvl, dtype=torch.int64, device=device))
+        if len(_PIXEL_CENTRES) > 16:
+            _PIXEL_CENTRES.clear()
+        hit = _PIXEL_CENTRES[key] = tuple(torch.cat(t) for t in (gx, gy, sw, sh, lv))
+    return hit
+
+
 class DeformableTransformerEncoder(nn.Module):
     def __init__(self, encoder_layer, num_layers):
         super().__init__()
@@ -114,18 +139,15 @@ class DeformableTransformerEncoder(nn.Module):
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device):
         """(N, S, L, 2): pixel centres of every query's own level, divided by that level's valid extent and
-        re-scaled to every level's valid ratio (:268-281).  ``spatial_shapes`` is iterated on the host, as in
-        the reference (one small device->host copy per call)."""
-        per_level = []
-        shapes = _shapes_on_host(spatial_shapes)
-        for lvl, (h, w) in enumerate(shapes):
-            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
-            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)
-            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
-            gy = gy.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * h)
-            gx = gx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * w)
-            per_level.append(torch.stack((gx, gy), -1))
-        points = torch.cat(per_level, 1)
+        re-scaled to every level's valid ratio (:268-281).  Same arithmetic, element by element, as the reference's
+        per-level loop (centre / (valid_ratio * size), then * valid_ratios) -- but the part that depends only on the
+        shapes (linspace + meshgrid per level, ~8 launches each) is built once per shapes tensor and the rest runs on
+        the concatenated levels: 7 launches per call instead of ~40 (0.5 ms of host time per eager step)."""
+        gx, gy, size_w, size_h, level_of = _pixel_centres(spatial_shapes, torch.device(device))
+        vr = valid_ratios.index_select(1, level_of)                      # (N, S, 2): the query's own level
+        ref_x = gx[None] / (vr[..., 0] * size_w)
+        ref_y = gy[None] / (vr[..., 1] * size_h)
+        points = torch.stack((ref_x, ref_y), -1)
         return points[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):

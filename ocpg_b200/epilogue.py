@@ -32,7 +32,7 @@ LN_CHANNELS = (128, 256, 512, 1024)
 
 
 def _stream(t) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    return _lib.raw_stream(t.device)
 
 
 def supported(*tensors) -> bool:
@@ -46,7 +46,7 @@ def column_sum(x2d: torch.Tensor) -> torch.Tensor:
     """sum over rows of a contiguous (rows, C) fp32 matrix, C % 4 == 0."""
     rows, C = x2d.shape
     out = torch.empty(C, dtype=torch.float32, device=x2d.device)
-    with torch.cuda.device(x2d.device):
+    with _lib.on_device(x2d.device):
         rc = _lib.lib().msda_column_sum_f32(x2d.data_ptr(), rows, C, out.data_ptr(), _stream(x2d))
     _lib.check(rc, "msda_column_sum_f32")
     return out
@@ -63,7 +63,7 @@ def dropout_mask(rng: torch.Tensor, salt: int, p: float, shape) -> torch.Tensor:
     for d in shape:
         n *= int(d)
     keep = torch.empty(n, dtype=torch.uint8, device=rng.device)
-    with torch.cuda.device(rng.device):
+    with _lib.on_device(rng.device):
         rc = _lib.lib().msda_dropout_mask_u8(rng.data_ptr(), int(salt), float(p), n, keep.data_ptr(), _stream(rng))
     _lib.check(rc, "msda_dropout_mask_u8")
     return keep.view(*shape).bool()
@@ -79,7 +79,7 @@ class _BiasResidualLayerNorm(Function):
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
         drop = rng is not None and p > 0.0
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             if drop:
                 rc = _lib.lib().msda_epilogue_ln_dropout_forward_f32(
                     x2.data_ptr(), None if bias is None else bias.data_ptr(), r2.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
@@ -106,7 +106,7 @@ class _BiasResidualLayerNorm(Function):
         dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
         dbias = torch.empty_like(gamma) if ctx.has_bias else None
         dx = dz
-        with torch.cuda.device(z.device):
+        with _lib.on_device(z.device):
             if ctx.drop is not None:
                 rng, (salt, p) = ctx.saved_tensors[4], ctx.drop
                 dx = torch.empty_like(z)
@@ -171,7 +171,7 @@ class _LinearReLU(Function):
         if rng is not None and p > 0.0:
             # dropout in place on the ReLU output: what is saved is dropout(relu(.)), whose sign pattern is the ReLU
             # mask AND the keep mask, so the backward needs neither the mask nor the generator
-            with torch.cuda.device(x.device):
+            with _lib.on_device(x.device):
                 rc = _lib.lib().msda_dropout_inplace_f32(h.data_ptr(), h.numel(), rng.data_ptr(), int(salt), float(p), _stream(x))
             _lib.check(rc, "msda_dropout_inplace_f32")
             ctx.p = float(p)
@@ -187,7 +187,7 @@ class _LinearReLU(Function):
         rows, C = g2.shape
         dpre = torch.empty_like(g2)
         gb = torch.empty(C, dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with _lib.on_device(g.device):
             if ctx.p > 0.0:
                 rc = _lib.lib().msda_relu_dropout_backward_column_sum_f32(g2.data_ptr(), h.data_ptr(), ctx.p, rows, C,
                                                                           dpre.data_ptr(), gb.data_ptr(), _stream(g))

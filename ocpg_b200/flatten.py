@@ -25,7 +25,7 @@ MAX_LEVELS = 8
 
 
 def _stream(t) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    return _lib.raw_stream(t.device)
 
 
 def _native_ok(tensors: Sequence[torch.Tensor]) -> bool:
@@ -57,7 +57,7 @@ def _flatten_native(srcs, poss, level_embed):
     if poss is not None:
         poss = [_aligned(t) for t in poss]
         pos_flat = torch.empty_like(src_flat)
-    with torch.cuda.device(src_flat.device):
+    with _lib.on_device(src_flat.device):
         rc = _lib.lib().msda_flatten_levels_f32(
             len(srcs), _ptr_array(srcs), None if poss is None else _ptr_array(poss),
             None if level_embed is None else level_embed.data_ptr(), _int_array(hs), _int_array(ws), N, C,
@@ -70,7 +70,7 @@ def _unflatten_native(flat, shapes):
     N, S, C = flat.shape
     flat = _aligned(flat)
     maps = [torch.empty(N, C, h, w, dtype=torch.float32, device=flat.device) for h, w in shapes]
-    with torch.cuda.device(flat.device):
+    with _lib.on_device(flat.device):
         rc = _lib.lib().msda_unflatten_levels_f32(len(shapes), flat.data_ptr(), _int_array([h for h, _ in shapes]),
                                                   _int_array([w for _, w in shapes]), N, C, S, _ptr_array(maps), _stream(flat))
     _lib.check(rc, "msda_unflatten_levels_f32")

@@ -163,3 +163,29 @@ def test_encoder_mirrors_reference_layout():
     ref = DeformableTransformerEncoder.get_reference_points(shapes, torch.ones(2, 2, 2), "cpu")
     assert ref.shape == (2, 16, 2, 2)
     assert torch.allclose(ref[0, 0, 0], torch.tensor([0.5 / 4, 0.5 / 3])) and torch.allclose(ref[0, 12, 1], torch.tensor([0.25, 0.25]))
+
+
+def test_encoder_reference_points_match_reference_loop():
+    """The cached / concatenated formulation gives, bit for bit, what the reference's per-level loop gives
+    (deformable_transformer.py:268-281), valid ratios < 1 included; a second call hits the cache."""
+    from ocpg_b200.encoder import DeformableTransformerEncoder
+    torch.manual_seed(0)
+    shapes = torch.tensor([(5, 7), (3, 4), (2, 2), (1, 1)])
+    vr = 0.5 + 0.5 * torch.rand(3, 4, 2)
+
+    def reference(spatial_shapes, valid_ratios):
+        out = []
+        for lvl, (H_, W_) in enumerate(spatial_shapes):
+            ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32),
+                                          torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32), indexing="ij")
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            out.append(torch.stack((ref_x, ref_y), -1))
+        pts = torch.cat(out, 1)
+        return pts[:, :, None] * valid_ratios[:, None]
+
+    want = reference(shapes, vr)
+    for _ in range(2):
+        got = DeformableTransformerEncoder.get_reference_points(shapes, vr, "cpu")
+        assert got.shape == want.shape == (3, 35 + 12 + 4 + 1, 4, 2) and torch.equal(got, want)
+    assert torch.equal(DeformableTransformerEncoder.get_reference_points(shapes.tolist(), vr, "cpu"), want)
