@@ -55,7 +55,7 @@ def parse_args():
                          "all-reduce of weight gradients (configs[2], [4]; tools/bench_encoder.py, its own metric)")
     ap.add_argument("--frames-per-gpu", type=int, default=0, help="encoder-* only")
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32", "bf16"], help="encoder-* only: GEMM precision policy")
-    ap.add_argument("--regime", default="init", choices=["init", "uniform"])
+    ap.add_argument("--regime", default="init", choices=["init", "uniform", "module_init"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--input-sets", type=int, default=6)
     ap.add_argument("--no-graph", action="store_true", help="launch from Python instead of CUDA graphs")

@@ -7,11 +7,23 @@
 //   (3) takes the 30 largest of the M*L*P = 128 attention weights per query (:372)      topk: sort-based, several launches
 //   (4) gathers the sampling locations of those 30                          (:375)      repeat + gather
 // on tensors of a few KB (config 4: 25 queries): pure launch latency.  Here (2)-(4) are ONE launch -- a warp per query
-// keeps the 128 weights in registers (4 per lane), extracts the top-k by repeated warp arg-max (k x 5 shuffle steps),
+// keeps the 128 weights in registers (4 per lane), extracts the top-k by repeated warp arg-max (two redux.sync per element),
 // and only the k selected locations are ever divided -- and (1) is one launch.
 //
 // Order of the selection = torch.topk(sorted=True): descending weight; equal weights in ascending index order (torch
-// leaves the order of ties unspecified).  NaN weights are not ordered specially (softmax outputs have none).
+// leaves the order of ties unspecified); NaN counts as the largest value, as in torch.
+
+// Weights as order-preserving 32-bit keys (sign flip for positives, complement for negatives: NaN sorts last = largest,
+// like torch.topk), so that one redux.sync (a single warp-wide max instruction) finds the winner's weight and a second one
+// (min over the tied lanes' indices) its position: 2 warp reductions per extracted element instead of 5 x 2 dependent
+// shuffle steps -- the selection is a chain of `top` dependent iterations, so their latency is the kernel's run time.
+__device__ __forceinline__ uint32_t order_key(float w) {
+    const uint32_t b = __float_as_uint(w);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
 // ITEMS = ceil(K / 32) weights per lane; top <= 32 (lane t keeps the t-th winner).
 template <int ITEMS>
@@ -22,37 +34,31 @@ decoder_select_samples_kernel(const float *__restrict__ loc, const float *__rest
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (n, q)
     if (row >= rows) return;
-    float w[ITEMS];
+    uint32_t key[ITEMS];                  // 0 = taken / past the end (every real key is > 0 except one NaN pattern)
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int k = lane + 32 * j;
-        w[j] = k < K ? __ldg(attn + row * K + k) : -INFINITY;
+        key[j] = k < K ? order_key(__ldg(attn + row * K + k)) : 0u;
     }
-    uint32_t taken = 0;                   // bit j: this lane's item j was selected
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-        if (lane + 32 * j >= K) taken |= 1u << j;
-    float my_w = 0.f;
+    uint32_t my_key = 0;
     int my_k = 0;
     for (int t = 0; t < top; ++t) {
-        // this lane's best remaining item (lowest index among equals: ascending j = ascending k)
-        float bw = -INFINITY;
-        int bk = 0x7fffffff;
+        uint32_t best = key[0];
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const bool free_ = !((taken >> j) & 1u);
-            if (free_ && (bk == 0x7fffffff || w[j] > bw)) { bw = w[j]; bk = lane + 32 * j; }
-        }
-        // warp arg-max on (weight desc, index asc)
+        for (int j = 1; j < ITEMS; ++j) best = max(best, key[j]);
+        const uint32_t m = __reduce_max_sync(0xffffffffu, best);
+        // among the lanes that hold the maximum: the smallest index (ascending j = ascending k within a lane)
+        int cand = 0x7fffffff;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const float ow = __shfl_xor_sync(0xffffffffu, bw, s);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, s);
-            const bool better = ok != 0x7fffffff && (bk == 0x7fffffff || ow > bw || (ow == bw && ok < bk));
-            if (better) { bw = ow; bk = ok; }
+        for (int j = ITEMS - 1; j >= 0; --j)
+            if (key[j] == m) cand = lane + 32 * j;
+        const int win = (int)__reduce_min_sync(0xffffffffu, (uint32_t)cand);
+        if ((win & 31) == lane) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (j == (win >> 5)) key[j] = 0u;
         }
-        if ((bk & 31) == lane && bk != 0x7fffffff) taken |= 1u << (bk >> 5);
-        if (lane == t) { my_w = bw; my_k = bk; }
+        if (lane == t) { my_key = m; my_k = win; }
     }
     if (lane < top) {
         const int n = (int)(row / Lq);
@@ -60,7 +66,7 @@ decoder_select_samples_kernel(const float *__restrict__ loc, const float *__rest
         const float2 s = __ldg(reinterpret_cast<const float2 *>(loc) + row * K + my_k);
         const float2 vr = __ldg(reinterpret_cast<const float2 *>(valid_ratios) + (int64_t)n * L + level);
         reinterpret_cast<float2 *>(samples_out)[row * top + lane] = make_float2(__fdiv_rn(s.x, vr.x), __fdiv_rn(s.y, vr.y));   // :368
-        if (weights_out) weights_out[row * top + lane] = my_w;
+        if (weights_out) weights_out[row * top + lane] = key_value(my_key);
         if (idx_out) idx_out[row * top + lane] = my_k;
     }
 }

@@ -122,6 +122,21 @@ def make_inputs(wl: Workload, regime: str = "init", seed: int = 0, device="cpu",
         wh = torch.stack((shapes[:, 1], shapes[:, 0]), -1).to(dtype)        # (L, 2) = (W, H)
         off = torch.randn(N, Lq, M, L, P, 2, **kw) * sigma_px
         loc = ref[None, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+    elif regime == "module_init":
+        # exactly what a freshly initialised MSDeformAttn produces (ms_deform_attn.py:62-74, :104-107): zero offset weights,
+        # offset bias = head m's compass direction (max-norm 1) times the point index 1..P, in pixels of every level;
+        # neighbouring queries therefore sample a regular lattice (spacing 1, 1/2, 1/4, 1/8 px at levels 0..3 for
+        # level-0 queries) -- far more row sharing between neighbours than the i.i.d. "init" regime
+        if Lq == S:
+            ref = encoder_reference_points(wl.levels, device, dtype)
+        else:
+            ref = torch.rand(Lq, 1, 2, **kw).expand(-1, L, -1)
+        ang = torch.arange(M, device=device, dtype=dtype) * (2.0 * math.pi / M)
+        direction = torch.stack([ang.cos(), ang.sin()], -1)
+        direction = direction / direction.abs().max(-1, keepdim=True)[0]                         # (M, 2)
+        off = direction.view(M, 1, 1, 2) * torch.arange(1, P + 1, device=device, dtype=dtype).view(1, 1, P, 1)
+        wh = torch.stack((shapes[:, 1], shapes[:, 0]), -1).to(dtype)
+        loc = (ref[None, :, None, :, None, :] + off.expand(M, L, P, 2)[None, None] / wh[None, None, None, :, None, :]).expand(N, Lq, M, L, P, 2)
     else:
         raise ValueError(f"unknown regime {regime!r}")
     attn = torch.softmax(torch.randn(N, Lq, M, L * P, **kw), -1).view(N, Lq, M, L, P)
