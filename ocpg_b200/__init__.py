@@ -1,9 +1,11 @@
 """ocpg_b200 -- B200-native (sm_100a) multi-scale deformable attention for TJUMMG/OCPG.
 
-A drop-in for the reference's ``models/ops`` package and nothing else:
+A drop-in for the reference's ``models/ops`` package and, around it, for the callers of that path in
+``models/deformable_transformer.py`` (section 8f):
 
     from ocpg_b200 import MSDeformAttn, MSDeformAttnFunction          # same API as models.ops.{modules,functions}
     import ocpg_b200.MultiScaleDeformableAttention as MSDA            # same functions as the pybind11 module
+    from ocpg_b200.transformer import DeformableTransformer           # encoder.py / decoder.py / flatten.py / epilogue.py
 
 Python/PyTorch host code calls hand-written CUDA kernels through the C ABI of include/msda_sm100.h
 (ctypes); no Triton, no multi-backend dispatch, no CPU fallback.

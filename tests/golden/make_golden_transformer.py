@@ -53,7 +53,9 @@ def load_reference():
 
 
 def param_projections(module, tag):
-    return {f"pgrad/{k}": tc.projection(f"{tag}/{k}", p.grad) for k, p in module.named_parameters()}
+    # parameters the graph never reaches (the refinement heads: their output is detached, :388) are recorded as NaN
+    return {f"pgrad/{k}": (tc.projection(f"{tag}/{k}", p.grad) if p.grad is not None else float("nan"))
+            for k, p in module.named_parameters()}
 
 
 def main():
@@ -87,6 +89,33 @@ def main():
                             grad_memory=memory.grad.numpy().astype(np.float32), grad_ref=refp.grad.numpy(),
                             **param_projections(dec, "dec"))
         print(name, tuple(hs.shape), tuple(samples.shape), float(hs.abs().max()))
+    full_transformer(dt)
+
+
+def full_transformer(dt):
+    """The whole DeformableTransformer (deformable_transformer.py:26-217), plus the decoder's iterative refinement branch
+    (:378-388) through a ``bbox_embed`` of plain Linears."""
+    torch.manual_seed(0)
+    for name, refine in (("full", False), ("full_refine", True)):
+        model = dt.DeformableTransformer(d_model=tc.D_MODEL, nhead=8, num_encoder_layers=tc.N_LAYERS, num_decoder_layers=tc.N_LAYERS,
+                                         dim_feedforward=tc.D_FFN, dropout=0.0, return_intermediate_dec=True).double()
+        if refine:
+            model.decoder.bbox_embed = torch.nn.ModuleList([torch.nn.Linear(tc.D_MODEL, 2) for _ in range(tc.N_LAYERS)]).double()
+        model.load_state_dict(tc.seeded_state_dict(model, "full"))
+        x = tc.full_inputs("full")
+        srcs = [s.clone().requires_grad_(True) for s in x["srcs"]]
+        tgt, qe = x["tgt"].clone().requires_grad_(True), x["query_embed"].clone().requires_grad_(True)
+        hs, memory_features, init_ref, inter_refs, _, _, inter_samples = model(srcs, tgt, x["masks"], x["pos_embeds"], qe)
+        loss_terms = [(hs * x["grad_hs"]).sum()] + [(m * g).sum() for m, g in zip(memory_features, x["grad_maps"])]
+        sum(loss_terms).backward()
+        out = dict(hs=hs.detach().numpy(), init_ref=init_ref.detach().numpy(), inter_refs=inter_refs.detach().numpy(),
+                   inter_samples=inter_samples.detach().numpy(), grad_tgt=tgt.grad.numpy(), grad_query_embed=qe.grad.numpy())
+        for i, m in enumerate(memory_features):
+            out[f"memory_{i}"] = m.detach().numpy().astype(np.float32)
+        for i, s_ in enumerate(srcs):
+            out[f"grad_src_{i}"] = s_.grad.numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, f"transformer_{name}.npz"), **out, **param_projections(model, "full"))
+        print(name, tuple(hs.shape), [tuple(m.shape) for m in memory_features], float(hs.abs().max()))
 
 
 if __name__ == "__main__":

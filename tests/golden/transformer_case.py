@@ -57,3 +57,23 @@ def projection(name: str, t: torch.Tensor) -> float:
     """<t, r> with r a fixed N(0,1) tensor named ``name``: a one-number fingerprint of a gradient."""
     r = torch.randn(t.shape, generator=_gen(f"proj/{name}"), dtype=torch.float64)
     return float((t.detach().double().cpu() * r).sum())
+
+
+def full_inputs(tag: str) -> dict:
+    """Inputs of DeformableTransformer.forward: per-level maps (b*t, c, h, w), padding masks with a valid top-left region
+    per frame (right / bottom padding like util/misc.py:nested_tensor_from_tensor_list), positional embeddings, the text
+    queries tgt (b, t, q, c) and the learned query embedding (q, c); plus cotangents for hs and the returned memory maps."""
+    g = lambda name, *shape: torch.randn(*shape, generator=_gen(f"{tag}/in/{name}"), dtype=torch.float64)
+    b, t = 1, N_FRAMES
+    valid = [(0.8, 0.9), (1.0, 0.7)]                      # per frame: (valid height, valid width) fraction
+    srcs, masks, poss = [], [], []
+    for l, (h, w) in enumerate(LEVELS):
+        srcs.append(g(f"src{l}", b * t, D_MODEL, h, w))
+        poss.append(0.1 * g(f"pos{l}", b * t, D_MODEL, h, w))
+        m = torch.ones(b * t, h, w, dtype=torch.bool)
+        for n, (fh, fw) in enumerate(valid):
+            m[n, :max(1, round(fh * h)), :max(1, round(fw * w))] = False
+        masks.append(m)
+    return dict(srcs=srcs, masks=masks, pos_embeds=poss, tgt=g("tgt", b, t, N_QUERIES, D_MODEL),
+                query_embed=g("qe", N_QUERIES, D_MODEL), grad_hs=g("ghs", N_LAYERS, b * t, N_QUERIES, D_MODEL),
+                grad_maps=[g(f"gmap{l}", b * t, D_MODEL, h, w) for l, (h, w) in enumerate(LEVELS[:-1])])

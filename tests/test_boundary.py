@@ -95,6 +95,9 @@ def test_reference_import_paths_resolve():
     import ocpg_b200
     assert MSDeformAttn is ocpg_b200.MSDeformAttn and MSDeformAttnFunction is ocpg_b200.MSDeformAttnFunction
     assert MSDA.ms_deform_attn_forward is ocpg_b200.MultiScaleDeformableAttention.ms_deform_attn_forward
+    from models.deformable_transformer import build_deforamble_transformer, DeformableTransformer      # ocpg.py:17
+    import ocpg_b200.transformer
+    assert DeformableTransformer is ocpg_b200.transformer.DeformableTransformer and callable(build_deforamble_transformer)
 
 
 def test_cpu_tensors_raise_like_the_reference():

@@ -176,3 +176,66 @@ def test_select_samples_ties_and_shapes(dev):
         from ocpg_b200 import _lib
         rc = ocpg_b200.lib().msda_decoder_select_samples_f32(1, 1, 1, 1, 1, 8, 4, 16, 30, 1, None, None, None)
         _lib.check(rc, "msda_decoder_select_samples_f32")
+
+
+# ---------------------------------------------------------------- the whole DeformableTransformer (:26-217)
+def _build_full(refine):
+    from ocpg_b200.transformer import DeformableTransformer
+    model = DeformableTransformer(d_model=tc.D_MODEL, nhead=8, num_encoder_layers=tc.N_LAYERS, num_decoder_layers=tc.N_LAYERS,
+                                  dim_feedforward=tc.D_FFN, dropout=0.0, return_intermediate_dec=True)
+    if refine:
+        model.decoder.bbox_embed = torch.nn.ModuleList([torch.nn.Linear(tc.D_MODEL, 2) for _ in range(tc.N_LAYERS)])
+    return model
+
+
+def test_full_transformer_mirrors_reference_layout():
+    g = load("full_refine")
+    model = _build_full(True)
+    assert set(model.state_dict()) == {k[len("pgrad/"):] for k in g if k.startswith("pgrad/")}
+    from ocpg_b200.transformer import build_deforamble_transformer
+    import types
+    args = types.SimpleNamespace(hidden_dim=256, nheads=8, enc_layers=1, dec_layers=1, dim_feedforward=64, dropout=0.1,
+                                 num_feature_levels=4, dec_n_points=4, enc_n_points=4, two_stage=False, num_queries=5)
+    m = build_deforamble_transformer(args)
+    assert m.decoder.return_intermediate and m.level_embed.shape == (4, 256) and m.reference_points.out_features == 2
+    with pytest.raises(NotImplementedError):
+        build_deforamble_transformer(types.SimpleNamespace(**{**vars(args), "two_stage": True}))
+    # valid ratios as the reference computes them (:125-133)
+    mask = torch.ones(2, 4, 6, dtype=torch.bool); mask[0, :3, :4] = False; mask[1, :, :3] = False
+    assert torch.equal(m.get_valid_ratio(mask), torch.tensor([[4 / 6, 3 / 4], [3 / 6, 1.0]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["full", "full_refine"])
+def test_full_transformer_vs_reference_golden(dev, case):
+    g = load(case)
+    model = _build_full(case == "full_refine")
+    model.load_state_dict({k: v.float() for k, v in tc.seeded_state_dict(model, "full").items()})
+    model = model.to(dev).train()
+    x = tc.full_inputs("full")
+    f32 = lambda t: t.float().to(dev)
+    srcs = [f32(s).requires_grad_(True) for s in x["srcs"]]
+    tgt, qe = f32(x["tgt"]).requires_grad_(True), f32(x["query_embed"]).requires_grad_(True)
+    masks, poss = [m.to(dev) for m in x["masks"]], [f32(p) for p in x["pos_embeds"]]
+    hs, memory_features, init_ref, inter_refs, a, b, inter_samples = model(srcs, tgt, masks, poss, qe)
+    assert a is None and b is None and len(memory_features) == 3
+    loss = (hs * f32(x["grad_hs"])).sum() + sum((m * f32(gm)).sum() for m, gm in zip(memory_features, x["grad_maps"]))
+    loss.backward()
+    assert rel(hs, g["hs"]) <= 2e-4, rel(hs, g["hs"])
+    assert rel(init_ref, g["init_ref"]) <= 1e-5 and rel(inter_refs, g["inter_refs"]) <= 1e-4
+    for i, m in enumerate(memory_features):
+        assert m.is_contiguous() and rel(m, g[f"memory_{i}"]) <= 2e-4, (i, rel(m, g[f"memory_{i}"]))
+    same = (inter_samples.double().cpu() - torch.from_numpy(g["inter_samples"])).abs().amax(-1) <= 1e-4
+    assert float(same.float().mean()) >= 0.95, float(same.float().mean())
+    assert rel(tgt.grad, g["grad_tgt"]) <= 2e-3 and rel(qe.grad, g["grad_query_embed"]) <= 2e-3
+    for i, s in enumerate(srcs):
+        assert rel(s.grad, g[f"grad_src_{i}"]) <= 2e-3, (i, rel(s.grad, g[f"grad_src_{i}"]))
+    for k, p in model.named_parameters():
+        want = float(g[f"pgrad/{k}"])
+        if want != want:                                    # NaN: the reference graph never reaches this parameter
+            assert p.grad is None, k
+            continue
+        got = tc.projection(f"full/{k}", p.grad)
+        assert abs(got - want) <= 5e-3 * (float(p.grad.double().norm()) + 1e-30), (k, got, want)
+    if case == "full_refine":                               # the refinement really moved the reference points
+        assert not np.allclose(g["inter_refs"], load("full")["inter_refs"])
