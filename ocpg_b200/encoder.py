@@ -26,6 +26,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import epilogue
+from ._shapes import remember_host_shapes, shapes_on_host as _shapes_on_host  # noqa: F401
 from .modules import MSDeformAttn
 
 
@@ -85,24 +86,6 @@ class DeformableTransformerEncoderLayer(nn.Module):
                                       level_start_index, padding_mask)[0]
         src = self.norm1(src + self.dropout1(attn_out))
         return self.forward_ffn(src)
-
-
-_HOST_SHAPES = {}      # (data_ptr, version, device) of a spatial_shapes tensor -> its rows as Python ints
-
-
-def _shapes_on_host(spatial_shapes):
-    """``spatial_shapes`` as a list of (H, W) ints.  The reference iterates the CUDA tensor (one device->host copy per
-    call, deformable_transformer.py:269); here the copy happens once per tensor (identity + version), which also keeps the
-    forward free of synchronisation so that a whole training step can be captured into a CUDA graph."""
-    if not isinstance(spatial_shapes, torch.Tensor):
-        return [tuple(int(v) for v in hw) for hw in spatial_shapes]
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, str(spatial_shapes.device), tuple(spatial_shapes.shape))
-    hit = _HOST_SHAPES.get(key)
-    if hit is None:
-        if len(_HOST_SHAPES) > 64:
-            _HOST_SHAPES.clear()
-        hit = _HOST_SHAPES[key] = [tuple(hw) for hw in spatial_shapes.tolist()]
-    return hit
 
 
 _PIXEL_CENTRES = {}

@@ -114,6 +114,8 @@ def flatten_levels(srcs: List[torch.Tensor], pos_embeds: Optional[List[torch.Ten
     lvl_pos_embed_flatten (N, S, C) or None, spatial_shapes (L, 2) int64 on the maps' device, level_start_index (L,))."""
     shapes = [tuple(t.shape[2:]) for t in srcs]
     spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=srcs[0].device)
+    from ._shapes import remember_host_shapes                 # the encoder needs (H, W) on the host: no copy back later
+    remember_host_shapes(spatial_shapes, shapes)
     level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
     tensors = list(srcs) + (list(pos_embeds) if pos_embeds is not None else []) + ([level_embed] if level_embed is not None else [])
     if _native_ok(list(srcs)) and all(t.is_cuda and t.dtype == torch.float32 for t in tensors):

@@ -29,6 +29,7 @@ from torch import nn
 
 from .. import MultiScaleDeformableAttention as MSDA
 from .. import epilogue
+from .._shapes import shapes_on_host
 from ..functions import MSDeformAttnFunction
 from ..functions.ms_deform_attn_func import MSDeformAttnFusedFunction
 
@@ -61,7 +62,6 @@ class MSDeformAttn(nn.Module):
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
-        self._shape_ok = {}            # (data_ptr, version, Len_in) of spatial_shapes tensors already verified
         self.fused = False             # True: softmax + sampling locations inside the kernels
         self.emit_sampling = True      # fused only: materialise sampling_locations / attention_weights for the caller
         self._reset_parameters()
@@ -85,13 +85,10 @@ class MSDeformAttn(nn.Module):
         nn.init.constant_(self.output_proj.bias.data, 0.0)
 
     def _check_shapes(self, spatial_shapes, len_in):
-        key = (spatial_shapes.data_ptr(), spatial_shapes._version, int(len_in))
-        if key not in self._shape_ok:
-            total = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())      # one sync, then cached
-            assert total == len_in, f"sum(H*W)={total} != Len_in={len_in}"       # reference :94
-            if len(self._shape_ok) > 64:
-                self._shape_ok.clear()
-            self._shape_ok[key] = True
+        """Reference :94 -- ``assert (H * W).sum() == Len_in`` -- on the host copy of the shapes: one device->host copy per
+        shapes tensor object and version (none at all for tensors built by ``flatten_levels``), not one per call."""
+        total = sum(h * w for h, w in shapes_on_host(spatial_shapes))
+        assert total == len_in, f"sum(H*W)={total} != Len_in={len_in}"
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):

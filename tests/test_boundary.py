@@ -192,3 +192,28 @@ def test_encoder_reference_points_match_reference_loop():
         got = DeformableTransformerEncoder.get_reference_points(shapes, vr, "cpu")
         assert got.shape == want.shape == (3, 35 + 12 + 4 + 1, 4, 2) and torch.equal(got, want)
     assert torch.equal(DeformableTransformerEncoder.get_reference_points(shapes.tolist(), vr, "cpu"), want)
+
+
+def test_host_shapes_cache_is_keyed_by_object_and_version():
+    """The host copy of spatial_shapes is reused only for the same tensor object at the same version: a new tensor (even at
+    a recycled address) or an in-place edit is read again; tensors built by flatten_levels never need the copy."""
+    from ocpg_b200._shapes import remember_host_shapes, shapes_on_host
+    a = torch.tensor([(3, 4), (2, 2)])
+    assert shapes_on_host(a) == [(3, 4), (2, 2)] and shapes_on_host(a) is shapes_on_host(a)
+    a[0, 0] = 5                                             # in-place: version bump
+    assert shapes_on_host(a) == [(5, 4), (2, 2)]
+    b = torch.tensor([(7, 1), (1, 1)])
+    assert shapes_on_host(b) == [(7, 1), (1, 1)]
+    assert shapes_on_host([(2, 3)]) == [(2, 3)] and shapes_on_host(torch.tensor([(2, 3)]).tolist()) == [(2, 3)]
+    c = remember_host_shapes(torch.tensor([(9, 9)]), [(9, 9)])
+    assert shapes_on_host(c) == [(9, 9)]
+    c[0, 1] = 8                                             # the tag is version-checked too
+    assert shapes_on_host(c) == [(9, 8)]
+    from ocpg_b200.flatten import flatten_levels
+    _, _, shapes, _ = flatten_levels([torch.zeros(1, 4, 2, 3), torch.zeros(1, 4, 1, 2)])
+    assert getattr(shapes, "_ocpg_host_shapes")[1] == [(2, 3), (1, 2)]
+    import ocpg_b200
+    m = ocpg_b200.MSDeformAttn(64, 2, 2, 2)
+    m._check_shapes(shapes, 8)
+    with pytest.raises(AssertionError):
+        m._check_shapes(shapes, 9)                          # reference :94
