@@ -14,4 +14,6 @@ python tools/bench_encoder.py --shape ytvos --gemm fp32 >> "$out" 2>> "${out%.js
 python tools/bench_encoder.py --shape ytvos --gemm tf32 >> "$out" 2>> "${out%.jsonl}.err"
 python tools/bench_encoder.py --shape ytvos --gemm tf32 --unfused >> "$out" 2>> "${out%.jsonl}.err"
 python tools/bench_encoder.py --shape ytvos --gemm bf16 >> "$out" 2>> "${out%.jsonl}.err"
+python tools/bench_encoder.py --shape ytvos --gemm tf32 --dropout 0.1 --graph >> "$out" 2>> "${out%.jsonl}.err"   # training setting, one CUDA graph
+python tools/bench_decoder.py --graph >> "$out" 2>> "${out%.jsonl}.err"                                        # configs[3] at layer level
 wc -l "$out"
