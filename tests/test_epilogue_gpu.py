@@ -202,3 +202,36 @@ def test_encoder_layer_dropout_runs_in_the_epilogue_kernels(dev):
     assert not layer._epilogue_ok(src)
     theirs = torch.stack([(layer(*args) - y_eval).square().mean() for _ in range(8)]).mean()
     assert abs(float(ours / theirs) - 1.0) < 0.15, (float(ours), float(theirs))
+
+
+def test_dropout_masks_change_between_cuda_graph_replays(dev):
+    """The dropout key words live in device memory and come from torch's graph-safe generator: a captured training step draws
+    a fresh mask on every replay (a mask baked into the graph would silently turn dropout into a fixed pruning)."""
+    from ocpg_b200 import epilogue
+    rows, C = 513, 256
+    x, res = torch.randn(rows, C, device=dev), torch.randn(rows, C, device=dev)
+    gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+
+    def f():
+        rng = epilogue.new_rng(dev)
+        return epilogue.bias_residual_layer_norm(x, None, res, gamma, beta, 1e-5, rng, 1, 0.5), rng
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        f()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y, rng = f()
+    outs, keys = [], []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        outs.append(y.clone()); keys.append(rng.clone())
+    assert not torch.equal(keys[0], keys[1]) and not torch.equal(keys[1], keys[2])
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    # and each replay is the reference formula under the mask of ITS key
+    keep = epilogue.dropout_mask(keys[2], 1, 0.5, (rows, C)).double()
+    want = F.layer_norm(res.double() + x.double() * keep / 0.5, (C,), gamma.double(), beta.double(), 1e-5)
+    assert rel(outs[2], want) <= 2e-6
