@@ -75,22 +75,15 @@ def main(argv=None):
 
     step, launches_per_step = eager_step, None
     if args.graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                eager_step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        for p in dec.parameters():
-            p.grad = None
-        memory.grad = tgt.grad = ref.grad = None
-        c0 = ocpg_b200.launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            eager_step()
-        launches_per_step = ocpg_b200.launch_count() - c0
-        step = graph.replay
+        from ocpg_b200.graph import GraphedStep
+        c0 = [0]
+
+        def counted_step():
+            c0[0] = ocpg_b200.launch_count()
+            return eager_step()
+        graphed = GraphedStep(counted_step, params=dec.parameters())
+        launches_per_step = ocpg_b200.launch_count() - c0[0]
+        step = graphed
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()

@@ -109,23 +109,18 @@ def main(argv=None):
         if world > 1:
             raise SystemExit("--graph: single GPU only")
         args.no_op_timing = True                 # CUDA events around library calls cannot be captured
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):            # warm-up off the default stream (allocator, cuBLAS handles, shape caches)
-            for _ in range(3):
-                eager_step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        for p in enc.parameters():
-            p.grad = None
-        c0 = ocpg_b200.launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            eager_step()
+        from ocpg_b200.graph import GraphedStep
+        c0 = None
+
+        def counted_step():
+            nonlocal c0
+            c0 = ocpg_b200.launch_count()
+            return eager_step()
+        graphed = GraphedStep(counted_step, params=enc.parameters())     # warm-up off the default stream, then one capture
         launches_per_step = ocpg_b200.launch_count() - c0
 
         def step():
-            graph.replay()
+            graphed()
             return 0
     for _ in range(args.warmup):
         step()
