@@ -217,3 +217,49 @@ def test_host_shapes_cache_is_keyed_by_object_and_version():
     m._check_shapes(shapes, 8)
     with pytest.raises(AssertionError):
         m._check_shapes(shapes, 9)                          # reference :94
+
+
+def test_side_kernel_argument_errors_do_not_touch_the_gpu():
+    """Every entry point around the operator validates before it launches: bad arguments return MSDA_ERR_* (and empty work
+    returns 0) without a device -- the C ABI's error contract (include/msda_sm100.h), checked here on the CPU."""
+    import ctypes
+    import ocpg_b200
+    L = ocpg_b200.lib()
+    INVALID, UNSUPPORTED = -1, -2
+    one = 4096                                              # any non-null, 16-byte aligned "pointer": never dereferenced
+    # epilogue
+    assert L.msda_epilogue_ln_forward_f32(one, None, one, one, one, 1e-5, 5, 100, one, one, one, one, None) == UNSUPPORTED
+    assert L.msda_epilogue_ln_forward_f32(one, None, one, one, one, 1e-5, -1, 256, one, one, one, one, None) == INVALID
+    assert L.msda_epilogue_ln_forward_f32(None, None, None, None, None, 1e-5, 0, 256, None, None, None, None, None) == 0
+    assert L.msda_epilogue_ln_forward_f32(one + 4, None, one, one, one, 1e-5, 5, 256, one, one, one, one, None) == INVALID
+    assert b"aligned" in L.msda_last_error()
+    assert L.msda_epilogue_ln_backward_f32(one, one, one, one, one, 5, 256, one, None, one, None, None) == INVALID   # no grad_gamma
+    assert L.msda_column_sum_f32(one, 5, 6, one, None) == INVALID                                                     # channels % 4
+    # dropout
+    assert L.msda_epilogue_ln_dropout_forward_f32(one, None, one, one, one, 1e-5, 5, 256, None, 1, 0.1, one, one, one, one, None) == INVALID
+    assert L.msda_epilogue_ln_dropout_forward_f32(one, None, one, one, one, 1e-5, 5, 256, one, 1, 1.0, one, one, one, one, None) == INVALID
+    assert b"[0, 1)" in L.msda_last_error()
+    assert L.msda_dropout_inplace_f32(one, 6, one, 1, 0.1, None) == INVALID                                           # n % 4
+    assert L.msda_dropout_inplace_f32(None, 0, one, 1, 0.1, None) == 0
+    assert L.msda_relu_dropout_backward_column_sum_f32(one, one, -0.5, 5, 8, one, one, None) == INVALID
+    assert L.msda_dropout_mask_u8(one, 1, 0.5, 8, None, None) == INVALID
+    # decoder consumers
+    assert L.msda_decoder_select_samples_f32(one, one, one, 1, 1, 8, 4, 4, 33, one, None, None, None) == UNSUPPORTED  # top > 32
+    assert L.msda_decoder_select_samples_f32(one, one, one, 1, 1, 8, 4, 16, 30, one, None, None, None) == UNSUPPORTED # K = 512
+    assert L.msda_decoder_select_samples_f32(one, one, one, 1, 1, 1, 2, 2, 5, one, None, None, None) == UNSUPPORTED   # top > K
+    assert L.msda_decoder_select_samples_f32(None, None, None, 0, 5, 8, 4, 4, 30, None, None, None, None) == 0
+    assert L.msda_decoder_select_samples_f32(None, one, one, 1, 1, 8, 4, 4, 30, one, None, None, None) == INVALID
+    assert L.msda_decoder_reference_points_f32(one, one, 1, 1, 4, 3, one, None) == INVALID                            # ref_dim
+    assert L.msda_decoder_reference_points_f32(one + 8, one, 1, 1, 4, 4, one, None) == INVALID                        # 16-byte alignment for boxes
+    # flattening
+    hw = (ctypes.c_int * 2)(4, 4)
+    ptrs = (ctypes.c_void_p * 2)(one, one)
+    assert L.msda_flatten_levels_f32(9, ptrs, None, None, hw, hw, 1, 8, one, None, None) == UNSUPPORTED
+    assert L.msda_flatten_levels_f32(2, ptrs, None, None, None, hw, 1, 8, one, None, None) == INVALID
+    assert L.msda_flatten_levels_f32(2, ptrs, ptrs, None, hw, hw, 1, 8, one, None, None) == INVALID                   # pos without pos_flatten
+    assert L.msda_flatten_levels_f32(2, ptrs, None, None, hw, hw, 0, 8, None, None, None) == 0
+    bad = (ctypes.c_void_p * 2)(one, None)
+    assert L.msda_flatten_levels_f32(2, bad, None, None, hw, hw, 1, 8, one, None, None) == INVALID
+    assert L.msda_unflatten_levels_f32(2, one, hw, hw, 1, 8, 10, ptrs, None) == INVALID                               # spatial_size < pixels
+    odd = (ctypes.c_void_p * 2)(one + 4, one)
+    assert L.msda_unflatten_levels_f32(2, one, hw, hw, 1, 8, 0, odd, None) == INVALID                                 # 16-byte kernels need alignment

@@ -112,3 +112,25 @@ def test_flatten_argument_errors(dev):
     assert L.msda_flatten_levels_f32(1, None, None, None, one, one, 1, 8, None, None, None) == -1
     bad = (ctypes.c_int * 1)(0)
     assert L.msda_unflatten_levels_f32(1, None, bad, one, 1, 8, 0, None, None) == -1
+
+
+@pytest.mark.gpu
+def test_flatten_random_shapes(dev):
+    """40 random pyramids (1-8 levels, odd and even sizes, channel counts that are and are not multiples of 4 / 32): both
+    kernel families (4-byte and 16-byte) against the reference statements, forward and inverse, bit for bit."""
+    import random
+    from ocpg_b200.flatten import flatten_levels, unflatten_levels
+    rnd = random.Random(7)
+    for case in range(40):
+        L = rnd.randint(1, 8)
+        even = case % 2 == 0
+        levels = [(rnd.randint(1, 20) * (2 if even else 1), rnd.randint(1, 20) * (2 if even else 1)) for _ in range(L)]
+        C = rnd.choice([4, 12, 32, 64, 100] if even else [1, 3, 12, 33, 64])
+        N = rnd.randint(1, 3)
+        srcs, poss, le = make(levels, N, C, dev, seed=case)
+        s, p, shapes, start = flatten_levels(srcs, poss, le)
+        rs, rp = reference_flatten(srcs, poss, le)
+        assert torch.equal(s, rs) and torch.equal(p, rp), (case, levels, C)
+        keep = levels[:max(1, L - 1)]
+        for a, b in zip(unflatten_levels(rs, keep), reference_unflatten(rs, keep)):
+            assert torch.equal(a, b), (case, levels, C)

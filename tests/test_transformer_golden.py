@@ -239,3 +239,35 @@ def test_full_transformer_vs_reference_golden(dev, case):
         assert abs(got - want) <= 5e-3 * (float(p.grad.double().norm()) + 1e-30), (k, got, want)
     if case == "full_refine":                               # the refinement really moved the reference points
         assert not np.allclose(g["inter_refs"], load("full")["inter_refs"])
+
+
+@pytest.mark.gpu
+def test_select_samples_random_with_ties(dev):
+    """Weights quantised to a few values (many exact ties) and random sizes: the selected weights equal torch.topk's, the
+    indices are distinct, point at those weights, and among equal weights come in ascending order."""
+    import random
+    from ocpg_b200.decoder import select_top_samples
+    rnd = random.Random(3)
+    for case in range(25):
+        M, L, P = rnd.choice([(8, 4, 4), (4, 4, 4), (2, 4, 8), (1, 3, 5), (8, 2, 16), (3, 1, 7)])
+        K = M * L * P
+        top = rnd.randint(1, min(32, K))
+        N, Lq = rnd.randint(1, 4), rnd.randint(1, 9)
+        levels_q = rnd.choice([2, 3, 5, 1000])
+        aw = (torch.rand(N, Lq, K, device=dev) * levels_q).floor().div(levels_q).view(N, Lq, M, L, P)
+        if case % 5 == 0:
+            aw = aw - 0.5                                   # negative weights order correctly too
+        loc = torch.rand(N, Lq, M, L, P, 2, device=dev)
+        vr = 0.5 + 0.5 * torch.rand(N, L, 2, device=dev)
+        keep, w, idx = select_top_samples(loc, aw, vr, top)
+        flat = aw.view(N, Lq, K)
+        tw, _ = flat.topk(top, dim=2)
+        assert torch.equal(w, tw), case
+        assert torch.equal(torch.gather(flat, 2, idx), w)
+        srt = idx.sort(-1).values
+        assert bool((srt[..., 1:] != srt[..., :-1]).all()) if top > 1 else True
+        if top > 1:
+            tie = w[..., 1:] == w[..., :-1]
+            assert bool((idx[..., 1:][tie] > idx[..., :-1][tie]).all()), case
+        want = torch.gather((loc / vr[:, None, None, :, None, :]).view(N, Lq, K, 2), 2, idx[..., None].expand(-1, -1, -1, 2))
+        assert torch.equal(keep, want)
