@@ -29,7 +29,7 @@ __device__ __forceinline__ uint32_t lcg(uint32_t &s) {
     return s >> 8;
 }
 
-enum Mode { LDG128 = 0, LDG256 = 1, LDG32 = 2, LDS128 = 3, RED128 = 4, RED32 = 5, LDG128_NC = 6, LDG64 = 7, ST128 = 8, RED64 = 9 };
+enum Mode { LDG128 = 0, LDG256 = 1, LDG32 = 2, LDS128 = 3, RED128 = 4, RED32 = 5, LDG128_NC = 6, LDG64 = 7, ST128 = 8, RED64 = 9, LDG128_HALF = 10, LDG64_HALF = 11 };
 
 // window_rows: power of two.  shared_window: 0 -> each CTA has its own window (L1-resident when small),
 // 1 -> all CTAs draw from the same window of window_rows rows (L2).
@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(kThreads) bench(float *buf, int window_rows, i
     const uint32_t mask = window_rows - 1;
     int grp, sub_bytes;
     if (MODE == LDG256) { grp = lane >> 2; sub_bytes = (lane & 3) * 32; }
+    else if (MODE == LDG128_HALF) { grp = lane >> 2; sub_bytes = (lane & 3) * 16; }      // 8 rows, the first 64 B of each (a bf16 row)
+    else if (MODE == LDG64_HALF) { grp = lane >> 3; sub_bytes = (lane & 7) * 8; }        // 4 rows, the first 64 B of each
     else if (MODE == LDG32 || MODE == RED32) { grp = 0; sub_bytes = lane * 4; }
     else if (MODE == LDG64 || MODE == RED64) { grp = lane >> 4; sub_bytes = (lane & 15) * 8; }
     else { grp = lane >> 3; sub_bytes = (lane & 7) * 16; }
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) bench(float *buf, int window_rows, i
         for (int u = 0; u < kUnroll; ++u) off[u] = (lcg(seed) & mask) * 128u + sub_bytes;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            if (MODE == LDG128) {
+            if (MODE == LDG128 || MODE == LDG128_HALF) {
                 const float4 v = __ldg(reinterpret_cast<const float4 *>(base + off[u]));
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             } else if (MODE == LDG128_NC) {
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kThreads) bench(float *buf, int window_rows, i
                 asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                              : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g), "=f"(h) : "l"(base + off[u]));
                 acc.x += a + e; acc.y += b + f; acc.z += c + g; acc.w += d + h;
-            } else if (MODE == LDG64) {
+            } else if (MODE == LDG64 || MODE == LDG64_HALF) {
                 const float2 v = __ldg(reinterpret_cast<const float2 *>(base + off[u]));
                 acc.x += v.x; acc.y += v.y;
             } else if (MODE == ST128) {
@@ -190,7 +192,7 @@ void run(const char *name, float *buf, size_t buf_bytes, int window_rows, int sh
             free(h);
         }
     }
-    const int rows_per_instr = MODE == LDG256 ? 8 : (MODE == LDG32 || MODE == RED32) ? 1 : (MODE == LDG64 || MODE == RED64) ? 2 : 4;
+    const int rows_per_instr = (MODE == LDG256 || MODE == LDG128_HALF) ? 8 : (MODE == LDG32 || MODE == RED32) ? 1 : (MODE == LDG64 || MODE == RED64) ? 2 : 4;
     const double instr_per_sm = (double)ctas_per_sm * (kThreads / 32) * iters * kUnroll;
     const double rows_per_sm = instr_per_sm * rows_per_instr;
     const double bytes = rows_per_sm * sms * 128.0;
@@ -212,6 +214,15 @@ int main() {
     CK(cudaMalloc(&sink, 16));
     CK(cudaMalloc(&d_cycles, sizeof(long long) * sms * 32));
     const int iters = 400;
+    if (getenv("UBENCH_HALF")) {      // is the L1 cost of a request per 128-byte LINE touched or per BYTE delivered?  (bf16 rows are half lines)
+        for (int cps : {4, 8}) {
+            run<LDG128>("ldg128_4rows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "4 full rows per instruction (fp32 layout)");
+            run<LDG64_HALF>("ldg64_4halfrows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "4 half rows (64 B) per instruction: the bf16 kernels' shape; TBps column counts 128 B per row");
+            run<LDG128_HALF>("ldg128_8halfrows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "8 half rows (64 B) per instruction; TBps column counts 128 B per row");
+            run<LDG128_HALF>("ldg128_8halfrows_L2", buf, buf_bytes, 1 << 17, 1, cps, iters, sms, sink, d_cycles, "8 half rows per instruction, shared 16 MB window");
+        }
+        return 0;
+    }
     if (getenv("UBENCH_FULL")) {
     for (int cps : {2, 4, 8}) {
         run<LDG128>("ldg128_4rows_L1", buf, buf_bytes, 128, 0, cps, iters, sms, sink, d_cycles, "private 16 KB window per CTA");
