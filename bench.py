@@ -71,10 +71,12 @@ def pick_workload(name):
 
 
 def measured_traffic(wl_name, regime, dtype):
-    """DRAM bytes per launch of the two kernels from the committed ncu capture (profiles/traffic.json), or None."""
+    """DRAM bytes per launch of the two kernels from the committed ncu capture (profiles/traffic.json), or None.
+    ``measured_traffic("_on_chip", None, None)`` returns the measured on-chip ceilings stored next to them."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(f"{wl_name}|{regime}|{dtype}")
+            table = json.load(f)
+        return table.get(wl_name) if wl_name.startswith("_") else table.get(f"{wl_name}|{regime}|{dtype}")
     except Exception:
         return None
 
@@ -414,6 +416,19 @@ def run_ours(args):
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
+        # The two on-chip resources that actually bound the kernels, from counters of the committed ncu
+        # capture and this run's launch times: informative, next to the contractual HBM roofline above.
+        on_chip = None
+        if traffic.get("bwd_red_bytes") and traffic.get("fwd_l1_lines"):
+            oc = measured_traffic("_on_chip", None, None) or {}
+            sms, mhz = torch.cuda.get_device_properties(dev).multi_processor_count, (clk or {}).get("sm_mhz") or 1965.0
+            red_gbs = traffic["bwd_red_bytes"] / (bwd_ms * 1e-3) / 1e9
+            line_rate = traffic["fwd_l1_lines"] / (fwd_ms * 1e-3) / (sms * mhz * 1e6)
+            on_chip = {"bwd": {"bound": "L2 fp32 atomic units", "achieved": red_gbs, "peak": oc.get("l2_fp32_atomic_peak_gbs"),
+                               "unit": "GB/s of red sectors", "frac": red_gbs / oc["l2_fp32_atomic_peak_gbs"] if oc.get("l2_fp32_atomic_peak_gbs") else None},
+                       "fwd": {"bound": "L1 line rate (gather only, without the per-point broadcasts)", "achieved": line_rate,
+                               "peak": oc.get("l1_lines_per_clk_per_sm"), "unit": "128-byte lines per clock per SM", "frac": line_rate},
+                       "source": oc.get("source")}
         line = {
             "metric": METRIC, "value": value_qps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -432,6 +447,7 @@ def run_ours(args):
             "roofline_fwd": {"kernel": "msda_fwd_tiled", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "traffic": traffic.get("fwd"),
                              "algorithmic_bytes": fwd_bytes, "launch_ms": fwd_ms, "launch_ms_min": fwd_min},
             "roofline_step": {"achieved": step_gbs, "frac": step_gbs / peak, "algorithmic_bytes": fwd_bytes + bwd_bytes},
+            "on_chip_ceilings": on_chip,
             "cpu_baseline": cpu, "clocks": clk,
         }
         print(json.dumps(line), flush=True)
