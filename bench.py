@@ -70,6 +70,12 @@ def pick_workload(name):
     return {"a2d": W.A2D_ENCODER, "ytvos": W.YTVOS_ENCODER, "decoder": W.A2D_DECODER}[name]
 
 
+def workload_config(wl, regime):
+    """The `config` object of the JSON line: the workload only, identical for both arms (run details go to `run`)."""
+    return {"workload": wl.name, "regime": regime, "frames_per_gpu": wl.n_frames, "levels": [list(l) for l in wl.levels],
+            "Lq": wl.n_queries, "M": wl.n_heads, "D": wl.head_dim, "L": wl.L, "P": wl.n_points}
+
+
 def measured_traffic(wl_name, regime, dtype):
     """DRAM bytes per launch of the two kernels from the committed ncu capture (profiles/traffic.json), or None.
     ``measured_traffic("_on_chip", None, None)`` returns the measured on-chip ceilings stored next to them."""
@@ -208,9 +214,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.name, "regime": args.regime, "frames_per_step": r["frames_per_step"],
-                   "levels": [list(l) for l in wl.levels], "Lq": wl.n_queries, "M": wl.n_heads, "D": wl.head_dim,
-                   "L": wl.L, "P": wl.n_points},
+        "config": workload_config(wl, args.regime),
+        "run": {"frames_per_step": r["frames_per_step"], "note": "each step is a bounded sample of the workload's frames (cpu_baseline.sample)"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -433,12 +438,11 @@ def run_ours(args):
             "metric": METRIC, "value": value_qps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": wl.name, "regime": args.regime, "frames_per_gpu": wl.n_frames,
-                       "levels": [list(l) for l in wl.levels], "Lq": wl.n_queries, "M": wl.n_heads, "D": wl.head_dim,
-                       "L": wl.L, "P": wl.n_points, "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                       "l2_policy": f"steps cycle through {R} distinct input sets of {set_bytes / 1e6:.0f} MB "
-                                    f"(+ as much output) each: inputs larger than L2 between reuses",
-                       "launch": "python" if graphs is None else "cuda-graph per step (fwd kernel, memset, bwd kernel)"},
+            "config": workload_config(wl, args.regime),
+            "run": {"parallelism": f"frames sharded over {world} GPU(s), no collective",
+                    "l2_policy": f"steps cycle through {R} distinct input sets of {set_bytes / 1e6:.0f} MB "
+                                 f"(+ as much output) each: inputs larger than L2 between reuses",
+                    "launch": "python" if graphs is None else "cuda-graph per step (fwd kernel, memset, bwd kernel)"},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "msda_bwd_tiled (+ the zero-fill of grad_value it needs)", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s",
                          "frac": bwd_gbs / peak, "traffic": traffic.get("bwd"), "traffic_source": traffic.get("source"),

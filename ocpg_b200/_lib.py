@@ -46,9 +46,9 @@ def _nvcc() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/msda_sm100.cu for sm_100a into ocpg_b200/lib/libmsda_sm100.so (cross-compiles
     without a GPU).  Rebuilds when the source or header is newer than the library."""
-    deps = [SRC, os.path.join(_PKG, "csrc", "msda_epilogue.cuh"), os.path.join(_PKG, "csrc", "msda_decoder.cuh"),
-            os.path.join(_PKG, "csrc", "msda_flatten.cuh"),
-            os.path.join(INCLUDE, "msda_sm100.h")]
+    csrc = os.path.join(_PKG, "csrc")
+    deps = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(INCLUDE, "msda_sm100.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
         os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)

@@ -1,0 +1,446 @@
+// msda_bwd_sorted.cuh -- the aggregating backward (D = 32): grad_value contributions are summed per DISTINCT row
+// inside a CTA tile before they are sent to L2 as vector reds.  Included by msda_sm100.cu.
+//
+// Implements ms_deform_im2col_cuda.cuh:301-403 (col2im) + :87-159 (bilinear gradients) of the reference, replacing its
+// four scalar atomics per thread and point (cuh:125-152) by one `red.global.add.v4.f32` per lane and RUN of up to four
+// items of the same row.
+//
+// Why.  Per (query, head) the backward touches 64 rows of `value` twice: it reads the row (for d/d location, d/d
+// attention) and adds a multiple of the query's grad_out row into the same row of grad_value.  In the encoder the 32
+// queries of an 8 x 4 tile of one head sample the same few hundred rows over and over: 77 % of the tile's valid
+// (query, point, corner) items hit a row that another item of the tile also hits (tools/experiments/duplicate_rows.py).
+// The query-major kernel (msda_bwd_tiled) pays one L1 row load and one L2 red per ITEM -- 39.9 M red sectors for a 24.7 MB
+// tensor on the A2D shape, 80 % of the chip's L2 atomic throughput.  This kernel turns the tile ROW-major:
+//
+//   stage   every thread owns (query, point) pairs exactly as in msda_bwd_tiled; it derives the four corner items
+//           {row, query, a*w_corner} of each;
+//   sort    the tile's <= 2048 items are counting-sorted by row in shared memory (integer shared-memory atomics are
+//           native; float ones are a CAS loop).  The histogram covers a WINDOW of 24 x 16 cells per pyramid level,
+//           centred on the mean sampled pixel of the tile at that level.  A cell with c items becomes c/4 full RUNS of
+//           four item slots, one more run padded with a null item (weight 0) if three items remain, and otherwise
+//           c%4 LOOSE items; items outside their window are loose too, so any distribution of sampling locations is
+//           handled, just without merging;
+//   walk    each 8-lane group of a warp takes a run: it loads the row of `value` ONCE, then for each of the four items
+//           reads the query's grad_out row from shared memory (one LDS.128: the same data-path cost as the L1 load it
+//           replaces), accumulates  acc += (a*w) * grad_out  in registers and forms the corner dot product
+//           p = <grad_out, value_row>  (8-lane butterfly over the four items); then ONE red.v4 per lane.  Fixed trip
+//           count, no predicates, no divergence.  Loose items take the same path one at a time.  The dot products go
+//           back to the owners through shared memory;
+//   finish  the owner of a (query, point) combines its four p's exactly like msda_bwd_tiled (cuh:123-158 regrouped).
+//
+// Row loads and reds drop 2.4x on the A2D / YTVOS encoder shapes in the init regime (642 per tile instead of 1532); what
+// is left per item is one 128-byte shared-memory read and ~10 instructions.
+#pragma once
+
+// Window of the counting sort: kWinX x kWinY cells per level, kSortLevels levels (more levels: msda_bwd_tiled).
+// 24 x 16 = +-3 sigma of the init regime's 2-pixel offsets around an 8 x 4 query tile.
+constexpr int kWinX = 24, kWinY = 16, kWinCells = kWinX * kWinY, kSortLevels = 4;
+constexpr int kSortCells = kSortLevels * kWinCells;
+
+template <int ROUNDS> struct SortSmem {
+    static constexpr int kQueries = 32;                          // 8 warps x 4 queries
+    static constexpr int kPoints = ROUNDS * 8;                   // point slots per (query, head)
+    static constexpr int kItems = kQueries * kPoints * 4;        // (query, point, corner)
+    // Item slots.  Runs grow from the front (a cell of c items takes at most c + 1 <= 4c/3 run slots: full runs of
+    // four, and a fourth, null, slot when three items remain), loose items from the back, so 4/3 kItems slots always
+    // suffice; four more hold the null run the tail of the walk points at.
+    static constexpr int kSlots = (kItems * 4 / 3 + 15) / 16 * 16;
+    static constexpr uint32_t kDummySlot = kItems;               // p slot of the null items
+    LevelTable lt;
+    int win_x[kSortLevels], win_y[kSortLevels];                  // window origin of each level, this tile
+    int stat[kSortLevels][4];                                    // sum x0, sum y0, points in range (this tile)
+    uint32_t warp_tot[8];
+    uint32_t n_runs, n_win_loose, n_overflow, pad_;
+    alignas(16) uint2 hist[kSortCells];                          // per window cell: {items, runs before | loose items before << 16}
+    uint32_t rows[kItems];                                       // row (unit offset) of run r at [r], of loose item i at [kItems-1-i]
+    uint2 items[kSlots + 4];                                     // {grad_out row offset | p slot << 16, a * w_corner}
+    float4 go[kQueries][8];                                      // grad_out rows of the tile's queries, fp32
+    float4 p[kQueries * kPoints + 1];                            // per (query, point): the four corner dot products (+ dummy)
+};
+
+#ifndef MSDA_SORT_MINB
+#define MSDA_SORT_MINB 4      // resident CTAs per SM the register budget is set for (4 -> 64 registers; ~55 KB of shared memory each)
+#endif
+
+// One sample point as its owner keeps it across the phases.
+struct SortPoint {
+    int x0, y0;          // top-left corner pixel, in [-1, W-1] x [-1, H-1] when the point is in range
+    float lx, ly;
+    float aa;            // attention weight (0 when the point is out of range, cuh:288 / :365)
+    int valid;           // bit i: corner i lies inside the level
+    int level;
+};
+
+__device__ __forceinline__ SortPoint sort_point(float loc_x, float loc_y, float a, int H, int W, int level) {
+    SortPoint g;
+    const float fw = (float)W, fh = (float)H;
+    const float x = fmaf(loc_x, fw, -0.5f);          // cuh:285-286 as compiled (see point_geometry)
+    const float y = fmaf(loc_y, fh, -0.5f);
+    const bool in_range = (y > -1.f) && (x > -1.f) && (y < fh) && (x < fw);      // cuh:288; false for NaN / inf
+    const float xf = floorf(x), yf = floorf(y);
+    g.x0 = in_range ? (int)xf : 0;
+    g.y0 = in_range ? (int)yf : 0;
+    g.lx = in_range ? x - xf : 0.f;
+    g.ly = in_range ? y - yf : 0.f;
+    const bool xa = in_range && g.x0 >= 0, xb = in_range && g.x0 < W - 1;
+    const bool ya = g.y0 >= 0, yb = g.y0 < H - 1;
+    g.valid = (int)(xa && ya) | ((int)(xb && ya) << 1) | ((int)(xa && yb) << 2) | ((int)(xb && yb) << 3);
+    g.aa = g.valid ? a : 0.f;
+    g.level = level;
+    return g;
+}
+
+// window origin along one axis: centred on the mean, clamped into the level
+__device__ __forceinline__ int window_origin(int sum, int cnt, int win, int size) {
+    const int mean = cnt ? __float2int_rn(__fdividef((float)sum, (float)cnt)) : 0;
+    return max(min(mean - win / 2 + 1, size - win), 0);
+}
+
+template <typename VT, int ROUNDS, bool FUSED>
+__global__ void __launch_bounds__(256, MSDA_SORT_MINB)
+msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+                const int64_t *__restrict__ start, const float *__restrict__ loc, const float *__restrict__ attn,
+                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d,
+                FusedArgs fa) {
+    using IO = RowIO<VT>;
+    using Vec = typename IO::Vec;
+    using SM = SortSmem<ROUNDS>;
+    constexpr int WARPS = 8;
+    constexpr int kTaskQueries = Tile<WARPS>::kQueries;
+    constexpr uint32_t kFull = 0xffffffffu;
+    static_assert(kSortCells == 256 * 6 && kWinX == 4 * 6, "the scan gives every thread six x-adjacent cells");
+    SM &sm = *reinterpret_cast<SM *>(msda_smem);
+    LevelTable &lt = sm.lt;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int grp = lane >> 3, cl = lane & 7;
+    const int qloc = warp * 4 + grp;                 // this lane group's query inside the tile
+    const int pts = d.L * d.P;
+    const int pixel_units = d.M * 8;
+
+    load_level_table<WARPS>(lt, shapes, start, d.L, d.Lq);
+    if (tid == 0) sm.n_overflow = 0;
+    if (tid < 4) sm.items[SM::kSlots + tid] = make_uint2(SM::kDummySlot << 16, 0u);       // the null run
+    for (int i = tid; i < kSortCells; i += 256) sm.hist[i] = make_uint2(0u, 0u);
+    if (tid < kSortLevels * 4) (&sm.stat[0][0])[tid] = 0;
+    __syncthreads();
+    const bool tiled = d.tiled && lt.dense;
+
+    uint32_t lv = 0;     // level of this lane's point in each round, one byte per round
+    int l_lo[ROUNDS], l_hi[ROUNDS];      // levels present in round r (the same for every lane)
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        lv |= (uint32_t)min((8 * r + cl) / d.P, d.L - 1) << (8 * r);
+        l_lo[r] = min((8 * r) / d.P, d.L - 1);
+        l_hi[r] = min((8 * r + 7) / d.P, d.L - 1);
+    }
+
+    const int tiles = tiled ? lt.tile_cum[d.L] : (d.Lq + kTaskQueries - 1) / kTaskQueries;
+    for (TaskWalk t(d.N, d.M, tiles, d.fchunk, blockIdx.x, gridDim.x); t.next();) {
+        const int m = t.m;
+        const int q = select_query<WARPS>(tiled, d, lt, t.tile, warp, grp);
+        const int64_t row = ((int64_t)t.n * d.Lq + max(q, 0)) * d.M + m;
+        const int64_t slice = ((int64_t)t.n * d.S * d.M + m) * 8 + cl;      // unit offset of frame n, head m, this lane
+        const Vec *vb = reinterpret_cast<const Vec *>(value) + slice;
+        float4 *gb = reinterpret_cast<float4 *>(grad_value) + slice;
+
+        // ---- stage: grad_out row -> shared memory, this lane's points -> registers, window statistics ----
+        {
+            Row go{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            if (q >= 0) go = IO::load_stream(reinterpret_cast<const Vec *>(grad_out) + (row * 8 + cl));
+            sm.go[qloc][cl] = make_float4(go.lo.x, go.lo.y, go.hi.x, go.hi.y);
+        }
+        float2 xy[ROUNDS];
+        float a[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const bool on = q >= 0 && 8 * r + cl < pts;
+            xy[r] = make_float2(-4.f, -4.f);
+            a[r] = 0.f;
+            if (on) {
+                xy[r] = ld_stream_f2(loc + (row * pts + 8 * r + cl) * 2);
+                a[r] = ld_stream_f1(attn + row * pts + 8 * r + cl);
+            }
+        }
+        const int64_t nq = (int64_t)t.n * d.Lq + max(q, 0);
+        if constexpr (FUSED) {
+            FusedArgs fwd_only = fa;       // the backward re-derives probabilities and locations; it emits neither
+            fwd_only.loc_out = nullptr; fwd_only.attn_out = nullptr;
+            fused_softmax_and_locations<ROUNDS>(xy, a, q >= 0, cl, pts, lv, lt, d, fwd_only, nq, row);
+        }
+        SortPoint sp[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int l = (lv >> (8 * r)) & 0xff;
+            sp[r] = sort_point(xy[r].x, xy[r].y, a[r], lt.H[l], lt.W[l], l);
+            // mean top-left pixel of the tile's in-range points, per level
+            for (int l2 = l_lo[r]; l2 <= l_hi[r]; ++l2) {
+                const bool mine = sp[r].valid && l == l2;
+                const int sx = __reduce_add_sync(kFull, mine ? sp[r].x0 : 0);
+                const int sy = __reduce_add_sync(kFull, mine ? sp[r].y0 : 0);
+                const int sc = __reduce_add_sync(kFull, mine ? 1 : 0);
+                if (lane == 0 && sc) {
+                    atomicAdd(&sm.stat[l2][0], sx);
+                    atomicAdd(&sm.stat[l2][1], sy);
+                    atomicAdd(&sm.stat[l2][2], sc);
+                }
+            }
+        }
+        __syncthreads();                                                                        // S1: statistics complete
+
+        // ---- histogram: window origin per level, cell of each valid corner, rank inside the cell ----
+        int ox[ROUNDS], oy[ROUNDS];
+        uint32_t rank[ROUNDS][2];      // four 16-bit ranks per round
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int l = sp[r].level;
+            const int4 st = *reinterpret_cast<const int4 *>(sm.stat[l]);
+            ox[r] = window_origin(st.x, st.z, kWinX, lt.W[l]);
+            oy[r] = window_origin(st.y, st.z, kWinY, lt.H[l]);
+        }
+        if (tid < d.L) {      // the same origins, published for the scan
+            const int4 st = *reinterpret_cast<const int4 *>(sm.stat[tid]);
+            sm.win_x[tid] = window_origin(st.x, st.z, kWinX, lt.W[tid]);
+            sm.win_y[tid] = window_origin(st.y, st.z, kWinY, lt.H[tid]);
+        }
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int cbase = sp[r].level * kWinCells;
+            rank[r][0] = rank[r][1] = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool cv = (sp[r].valid >> c) & 1;
+                const int ux = sp[r].x0 + (c & 1) - ox[r], uy = sp[r].y0 + (c >> 1) - oy[r];
+                const bool inw = cv && (unsigned)ux < (unsigned)kWinX && (unsigned)uy < (unsigned)kWinY;
+                uint32_t rk = 0;
+                if (inw) rk = atomicAdd(&sm.hist[cbase + uy * kWinX + ux].x, 1u);
+                const bool ovf = cv && !inw;
+                const uint32_t bal = __ballot_sync(kFull, ovf);
+                if (bal) {      // warp-aggregated ticket for the items outside their window
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.n_overflow, (uint32_t)__popc(bal));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (ovf) rk = base + __popc(bal & ((1u << lane) - 1u));
+                }
+                rank[r][c >> 1] |= rk << (16 * (c & 1));
+            }
+        }
+        __syncthreads();                                                                        // S2: histogram complete
+
+        // ---- scan: a cell of c items = c/4 full runs, one more (null-padded) run if three items remain, else c%4 loose items ----
+        {
+            const int c0 = tid * 6;      // six x-adjacent cells of one window row
+            uint32_t cnt[6], tsum = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k += 2) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(&sm.hist[c0 + k]);
+                cnt[k] = v.x; cnt[k + 1] = v.z;
+            }
+            uint32_t pre[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {      // low half: runs, high half: loose items
+                pre[k] = tsum;
+                const uint32_t r = cnt[k] & 3u;
+                tsum += (cnt[k] >> 2) + (r == 3u ? 1u : r << 16);
+            }
+            uint32_t incl = tsum;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t o = __shfl_up_sync(kFull, incl, s);
+                if (lane >= s) incl += o;
+            }
+            if (lane == 31) sm.warp_tot[warp] = incl;
+            if (tid < kSortLevels * 4) (&sm.stat[0][0])[tid] = 0;       // statistics are dead after S2: reset for the next tile
+            __syncthreads();                                                                    // S3
+            uint32_t excl = incl - tsum;
+            for (int w = 0; w < warp; ++w) excl += sm.warp_tot[w];
+            if (tsum) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sm.hist[c0 + k].y = excl + pre[k];
+            }
+            if (tid == 255) {
+                sm.n_runs = (excl + tsum) & 0xffffu;
+                sm.n_win_loose = (excl + tsum) >> 16;
+            }
+        }
+        __syncthreads();                                                                        // S4: offsets complete
+
+        // ---- place: every item to its slot; the first item of a run also records the run's row ----
+        const int n_runs = (int)sm.n_runs;
+        const uint32_t n_win_loose = sm.n_win_loose;
+        const int n_loose = (int)(n_win_loose + sm.n_overflow);      // complete since S2; reset after S5
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int l = sp[r].level;
+            const int cbase = l * kWinCells;
+            const float hx = 1.f - sp[r].lx, hy = 1.f - sp[r].ly;
+            const float w4[4] = {hy * hx, hy * sp[r].lx, sp[r].ly * hx, sp[r].ly * sp[r].lx};
+            const uint32_t tag0 = (uint32_t)(qloc * 128) | ((uint32_t)((qloc * SM::kPoints + 8 * r + cl) * 4) << 16);
+            const int pixel00 = lt.start[l] + sp[r].y0 * lt.W[l] + sp[r].x0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (!((sp[r].valid >> c) & 1)) continue;
+                const int ux = sp[r].x0 + (c & 1) - ox[r], uy = sp[r].y0 + (c >> 1) - oy[r];
+                const bool inw = (unsigned)ux < (unsigned)kWinX && (unsigned)uy < (unsigned)kWinY;
+                const uint32_t rk = (rank[r][c >> 1] >> (16 * (c & 1))) & 0xffffu;
+                const uint32_t unit = (uint32_t)((pixel00 + (c & 1) + (c >> 1) * lt.W[l]) * pixel_units);
+                uint32_t li = n_win_loose + rk;      // loose index (items outside the window come after the window's)
+                uint32_t pos;
+                bool loose = true;
+                if (inw) {
+                    const uint2 h = sm.hist[cbase + uy * kWinX + ux];      // {items of the cell, runs before | loose before << 16}
+                    const uint32_t rem = h.x & 3u;
+                    const uint32_t run_items = rem == 3u ? h.x : h.x - rem;
+                    loose = rk >= run_items;
+                    li = (h.y >> 16) + rk - run_items;
+                    if (!loose) {
+                        const uint32_t run0 = h.y & 0xffffu;
+                        pos = 4 * run0 + rk;
+                        if (!(rk & 3u)) sm.rows[run0 + (rk >> 2)] = unit;
+                        if (rem == 3u && rk + 1 == h.x) sm.items[pos + 1] = make_uint2(SM::kDummySlot << 16, 0u);      // null item pads the run
+                    }
+                }
+                if (loose) {
+                    pos = SM::kSlots - 1 - li;
+                    sm.rows[SM::kItems - 1 - li] = unit;
+                }
+                sm.items[pos] = make_uint2(tag0 + ((uint32_t)c << 16), __float_as_uint(sp[r].aa * w4[c]));
+            }
+        }
+        __syncthreads();                                                                        // S5: items complete
+
+        // ---- walk ----
+        {
+            if (tid == 0) sm.n_overflow = 0;          // every thread read it before S5; its next writer comes after S1
+            // the histogram is dead: clear it for the next tile (its next writer comes after S6 / S1)
+            for (int i = tid; i < kSortCells / 2; i += 256) reinterpret_cast<uint4 *>(sm.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+            const char *go_lane = reinterpret_cast<const char *>(&sm.go[0][cl]);
+            float *p_flat = reinterpret_cast<float *>(sm.p);
+            auto go_row = [&](uint32_t tag) -> Row {
+                const float4 g4 = *reinterpret_cast<const float4 *>(go_lane + (tag & 0xffffu));
+                return Row{make_float2(g4.x, g4.y), make_float2(g4.z, g4.w)};
+            };
+            // runs: one per lane group, four items each, all of the same row
+            {
+                int run = warp * 4 + grp;
+                bool has = run < n_runs;
+                uint32_t unit = has ? sm.rows[run] : 0u;
+                const uint2 *ip = &sm.items[has ? 4 * run : SM::kSlots];
+                Row v = IO::load(row_at(vb, unit));
+#pragma unroll 2
+                for (int base = warp * 4; base < n_runs; base += 32) {
+                    run += 32;
+                    const bool has_next = run < n_runs;
+                    const uint32_t unit_next = has_next ? sm.rows[run] : 0u;
+                    const uint2 *ip_next = &sm.items[has_next ? 4 * run : SM::kSlots];
+                    const Row v_next = IO::load(row_at(vb, unit_next));      // next row in flight during this run
+                    Row acc{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                    float ds[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint2 it = ip[k];
+                        const Row g = go_row(it.x);
+                        fma_row(__uint_as_float(it.y), g, acc);      // grad_value[row] += (a * w_corner) * grad_out   (cuh:125,134,143,152)
+                        ds[k] = dot_row(g, v);                       // this lane's four channels of <grad_out, value row>
+                    }
+                    // reduce over the 8 lanes of the group: lanes 2j, 2j+1 end with the sum of item j
+                    const bool up4 = (cl & 4) != 0, up2 = (cl & 2) != 0;
+                    const float e0 = (up4 ? ds[2] : ds[0]) + __shfl_xor_sync(kFull, up4 ? ds[0] : ds[2], 4);
+                    const float e1 = (up4 ? ds[3] : ds[1]) + __shfl_xor_sync(kFull, up4 ? ds[1] : ds[3], 4);
+                    float tot = (up2 ? e1 : e0) + __shfl_xor_sync(kFull, up2 ? e0 : e1, 2);
+                    tot += __shfl_xor_sync(kFull, tot, 1);
+                    if (!(cl & 1)) p_flat[ip[cl >> 1].x >> 16] = tot;      // null items: the dummy slot
+                    if (has)
+                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                                     :: "l"(row_at(gb, unit)), "f"(acc.lo.x), "f"(acc.lo.y), "f"(acc.hi.x), "f"(acc.hi.y) : "memory");
+                    has = has_next; unit = unit_next; ip = ip_next; v = v_next;
+                }
+            }
+            // loose items: one per lane group and step, each with its own row; two steps in flight
+            for (int base = warp * 4; base < n_loose; base += 64) {
+                uint2 it[2];
+                uint32_t unit[2];
+                bool has[2];
+                Row v[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int li = base + 32 * u + grp;
+                    has[u] = li < n_loose;
+                    it[u] = sm.items[has[u] ? SM::kSlots - 1 - li : SM::kSlots];
+                    unit[u] = has[u] ? sm.rows[SM::kItems - 1 - li] : 0u;
+                    v[u] = IO::load(row_at(vb, unit[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const Row g = go_row(it[u].x);
+                    const float aw = __uint_as_float(it[u].y);
+                    float dsum = dot_row(g, v[u]);
+                    if (has[u]) {
+                        const float2 s0 = __fmul2_rn(splat(aw), g.lo), s1 = __fmul2_rn(splat(aw), g.hi);
+                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                                     :: "l"(row_at(gb, unit[u])), "f"(s0.x), "f"(s0.y), "f"(s1.x), "f"(s1.y) : "memory");
+                    }
+                    // same summation tree as the runs' butterfly (lane pairs 4 apart first): whether an item lands in a run or
+                    // here depends on the order of the histogram atomics, and d/d location, d/d attention stay bitwise reproducible
+                    dsum += __shfl_xor_sync(kFull, dsum, 4);
+                    dsum += __shfl_xor_sync(kFull, dsum, 2);
+                    dsum += __shfl_xor_sync(kFull, dsum, 1);
+                    if (cl == 0) p_flat[it[u].x >> 16] = dsum;
+                }
+            }
+        }
+        __syncthreads();                                                                        // S6: dot products complete
+
+        // ---- finish: the owner of a point combines its four corner dot products (cuh:123-158 regrouped by corner) ----
+        float g_prob[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            g_prob[r] = 0.f;
+            const int pt = 8 * r + cl;
+            if (!(q >= 0 && pt < pts)) continue;
+            const int l = sp[r].level;
+            const float4 ps = sm.p[qloc * SM::kPoints + pt];
+            const int valid = sp[r].valid;
+            const float lx = sp[r].lx, ly = sp[r].ly, a_own = sp[r].aa;
+            const float hx = 1.f - lx, hy = 1.f - ly;
+            // corners outside the level were never items: zero padding (cuh:56-78)
+            const float q00 = (valid & 1) ? ps.x : 0.f, q01 = (valid & 2) ? ps.y : 0.f;
+            const float q10 = (valid & 4) ? ps.z : 0.f, q11 = (valid & 8) ? ps.w : 0.f;
+            const float ga = (hy * hx) * q00 + (hy * lx) * q01 + (ly * hx) * q10 + (ly * lx) * q11;       // :156
+            const float gx = hy * (q01 - q00) + ly * (q11 - q10);                                         // :157
+            const float gy = hx * (q10 - q00) + lx * (q11 - q01);                                         // :158
+            const float2 gl = make_float2((float)lt.W[l] * a_own * gx, (float)lt.H[l] * a_own * gy);
+            if constexpr (!FUSED) {
+                grad_attn[row * pts + pt] = ga;
+                *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) = gl;
+            } else {
+                // d/d offsets through sampling_locations = ref + offsets / (W, H)            (ms_deform_attn.py:104-107)
+                //                          or           = ref_xy + offsets / P * ref_wh * 0.5   (:108-110)
+                g_prob[r] = ga;
+                if (fa.grad_loc_out) *reinterpret_cast<float2 *>(fa.grad_loc_out + (row * pts + pt) * 2) = gl;
+                float2 go_;
+                if (fa.ref_dim == 2) {
+                    go_ = make_float2(__fdiv_rn(gl.x, (float)lt.W[l]), __fdiv_rn(gl.y, (float)lt.H[l]));
+                } else {
+                    const float4 rp = __ldg(reinterpret_cast<const float4 *>(fa.ref) + (nq * d.L + l));
+                    const float fp = (float)d.P;
+                    go_ = make_float2(__fdiv_rn(__fmul_rn(__fmul_rn(gl.x, 0.5f), rp.z), fp),
+                                      __fdiv_rn(__fmul_rn(__fmul_rn(gl.y, 0.5f), rp.w), fp));
+                }
+                *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) = go_;
+            }
+        }
+        if constexpr (FUSED) {
+            // softmax gradient: d logit_i = p_i * (g_i - sum_j p_j g_j) over the L*P points of this (query, head)
+            float dot = 0.f;
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) dot = fmaf(a[r], g_prob[r], dot);
+            dot = group_sum(dot);
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r)
+                if (q >= 0 && 8 * r + cl < pts) grad_attn[row * pts + 8 * r + cl] = a[r] * (g_prob[r] - dot);
+        }
+        // no barrier here: the next tile's first shared-memory writes (go rows, statistics) touch nothing this phase
+        // reads, and S1 of the next tile orders everything else
+    }
+}

@@ -21,8 +21,10 @@
 //   3. locality: a CTA pass covers an 8x8 (or 8x4) spatial tile of queries of ONE head, whose rows overlap (L1);
 //   4. the backward's reds are predicated off for zero-weight corners, and the persistent CTAs are spread over
 //      all (frame, head) slices at once so that the coarse levels' few rows do not serialise in L2;
-//   5. the backward's per-point reductions go through shared memory (one STS.128 per point, a rotated 8-way
-//      add by the lane that owns the point) instead of 28 shuffles: fewer registers, 32 resident warps.
+//   5. the backward is ROW-major (msda_bwd_sorted.cuh): a CTA tile's (query, point, corner) items are counting-sorted
+//      by row in shared memory, every distinct row is loaded once and receives ONE vector red per lane; the
+//      query-major msda_bwd_tiled below (8-lane butterfly shuffles for the per-point reductions) serves the
+//      under-filled launches of the decoder.
 //
 // No tensor cores: the op is a gather / scatter with ~0.2 flop per byte.
 
@@ -47,11 +49,14 @@ std::atomic<int> g_fwd_ctas_per_sm{0};   // 0 = kernel default
 std::atomic<int> g_bwd_ctas_per_sm{0};
 std::atomic<int> g_fwd_warps{0};          // 0 = default; 8 or 16 warps per CTA
 std::atomic<int> g_bwd_warps{0};
-std::atomic<int> g_bwd_mode{0};          // experiments: see Dims::bwd_mode
+#ifdef MSDA_EXPERIMENTS                  // measurement-only switches: never in the product build (they return wrong gradients)
+std::atomic<int> g_bwd_mode{0};          // see Dims::bwd_mode
+std::atomic<int> g_skip_scatter{0};      // see Dims::debug_skip_scatter
+#endif
 std::atomic<int> g_unit{0};               // 0 = automatic; frames interleaved by the task walk
 std::atomic<int> g_force_generic{0};
 std::atomic<int> g_force_linear{0};     // experiments: never use the tiled query walk
-std::atomic<int> g_skip_scatter{0};     // experiments: see Dims::debug_skip_scatter
+std::atomic<int> g_bwd_algo{0};         // 0 = automatic (row-major "sorted" kernel unless the launch is under-filled), 1 = query-major msda_bwd_tiled
 std::atomic<int> g_bwd_deep{0};         // 0 = automatic (under-filled launches), 1 = always, -1 = never: msda_bwd_tiled<.., DEEP>
 
 int fail(int code, const char *msg) {
@@ -91,9 +96,11 @@ template <int WARPS> struct Tile {
 struct Dims {
     int N, S, M, L, Lq, P;       // D is 32 for the tiled kernels
     int tiled;                   // 1: Lq == S, walk queries as spatial tiles of their own level
-    int debug_skip_scatter;      // experiments only: backward omits the grad_value reds (wrong grad_value)
     int fchunk;                  // frames whose passes are interleaved (TaskWalk)
-    int bwd_mode;                // experiments only, see msda_bwd_tiled
+#ifdef MSDA_EXPERIMENTS
+    int debug_skip_scatter;      // msda_bwd_tiled omits the grad_value reds (wrong grad_value)
+    int bwd_mode;                // see msda_bwd_tiled
+#endif
 };
 
 struct LevelTable {              // shared memory, filled once per CTA from the int64 device tensors
@@ -515,7 +522,11 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
     // Dims::bwd_mode (measurement only): 1 = gather / reduce without the scatter, 2 = the scatter alone (no `value`
     // traffic at all).  Together they show what bounds the kernel: the scatter alone takes ~85 % of the full
     // backward -- the L2 atomic units, chip-wide.  0 = the real thing.
+#ifdef MSDA_EXPERIMENTS
     const bool scatter = d.bwd_mode != 1 && !d.debug_skip_scatter, gather = d.bwd_mode != 2;
+#else
+    constexpr bool scatter = true, gather = true;
+#endif
     const int rank = blockIdx.x, workers = gridDim.x;
     uint32_t lv = 0;     // level of this lane's point in each round, one byte per round
 #pragma unroll
@@ -674,6 +685,9 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
                     *reinterpret_cast<float2 *>(grad_loc + (row * pts + pt) * 2) = go_;
                 }
             }
+            // the staging slots are rewritten by the next round: order this round's shared-memory reads before those
+            // writes (the shuffles above give no memory ordering)
+            __syncwarp();
         }
         if constexpr (FUSED) {
             // softmax gradient: d logit_i = p_i * (g_i - sum_j p_j g_j) over the L*P points of this (query, head)
@@ -685,7 +699,6 @@ msda_bwd_tiled(const VT *__restrict__ grad_out, const VT *__restrict__ value, co
             for (int r = 0; r < ROUNDS; ++r)
                 if (q >= 0 && 8 * r + cl < pts) grad_attn[row * pts + 8 * r + cl] = a[r] * (g_prob[r] - dot);
         }
-        __syncwarp();
     }
 }
 
@@ -701,6 +714,7 @@ __global__ void msda_f32_to_bf16(const float4 *__restrict__ src, uint2 *__restri
     }
 }
 
+#include "msda_bwd_sorted.cuh"
 #include "msda_epilogue.cuh"
 #include "msda_decoder.cuh"
 #include "msda_flatten.cuh"
@@ -837,8 +851,15 @@ int frame_chunk(int N, int S, int M, int D, int elem_bytes) {
 }
 
 Dims make_dims(int N, int S, int M, int D, int L, int Lq, int P, int elem_bytes) {
-    return Dims{N, S, M, L, Lq, P, (Lq == S && !g_force_linear.load()) ? 1 : 0, g_skip_scatter.load(),
-                frame_chunk(N, S, M, D, elem_bytes), g_bwd_mode.load()};
+    Dims d{};
+    d.N = N; d.S = S; d.M = M; d.L = L; d.Lq = Lq; d.P = P;
+    d.tiled = (Lq == S && !g_force_linear.load()) ? 1 : 0;
+    d.fchunk = frame_chunk(N, S, M, D, elem_bytes);
+#ifdef MSDA_EXPERIMENTS
+    d.debug_skip_scatter = g_skip_scatter.load();
+    d.bwd_mode = g_bwd_mode.load();
+#endif
+    return d;
 }
 
 bool tiled_ok(int channels, int L, int P) {
@@ -933,6 +954,32 @@ int launch_bwd_kernel(int grid, const VT *go, const VT *value, const int64_t *sh
     return after_launch("msda_bwd_tiled");
 }
 
+// The row-major backward (msda_bwd_sorted.cuh): one wave of as many CTAs as fit (registers / ~51 KB of shared memory each).
+template <typename K>
+int resident_ctas(K kernel, int threads, size_t smem, int fallback) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm <= 0) per_sm = fallback;
+    return per_sm;
+}
+template <typename VT, int ROUNDS>
+int launch_bwd_sorted(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
+                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
+    const size_t smem = sizeof(SortSmem<ROUNDS>);
+    const int knob = g_bwd_ctas_per_sm.load();
+    if (fa) {
+        auto kernel = msda_bwd_sorted<VT, ROUNDS, true>;
+        if (const int rc = configure(kernel, smem)) return rc;
+        const int grid = sm_count() * (knob > 0 ? knob : resident_ctas(kernel, 256, smem, 1));
+        kernel<<<grid, 256, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, *fa);
+    } else {
+        auto kernel = msda_bwd_sorted<VT, ROUNDS, false>;
+        if (const int rc = configure(kernel, smem)) return rc;
+        const int grid = sm_count() * (knob > 0 ? knob : resident_ctas(kernel, 256, smem, 1));
+        kernel<<<grid, 256, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, FusedArgs{});
+    }
+    return after_launch("msda_bwd_sorted");
+}
+
 // The decoder's shapes (a handful of queries per frame) give fewer passes than one wave has CTAs: those launches use
 // the DEEP instantiation (8 warps, one CTA per SM, every row load of a round in flight at once).
 template <typename VT, int ROUNDS, int WARPS>
@@ -944,6 +991,9 @@ int launch_bwd_one(const VT *go, const VT *value, const int64_t *shapes, const i
         const int deep = g_bwd_deep.load();
         if (deep > 0 || (deep == 0 && passes <= 2 * (int64_t)sm_count()))
             return launch_bwd_kernel<VT, ROUNDS, 8, true>(sm_count(), go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
+    }
+    if constexpr (WARPS == 8) {
+        if (g_bwd_algo.load() != 1 && d.L <= kSortLevels) return launch_bwd_sorted<VT, ROUNDS>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
     }
     return launch_bwd_kernel<VT, ROUNDS, WARPS, false>(grid, go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
 }
@@ -1017,14 +1067,20 @@ int msda_set_option(const char *key, int value) {
     if (!key) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_set_option: null key");
     if (!strcmp(key, "fwd_ctas_per_sm")) { g_fwd_ctas_per_sm = value; return MSDA_OK; }
     if (!strcmp(key, "bwd_ctas_per_sm")) { g_bwd_ctas_per_sm = value; return MSDA_OK; }
-    if (!strcmp(key, "bwd_mode")) { g_bwd_mode = value; return MSDA_OK; }
     if (!strcmp(key, "frame_chunk")) { g_unit = value; return MSDA_OK; }
     if (!strcmp(key, "fwd_warps")) { g_fwd_warps = value; return MSDA_OK; }
     if (!strcmp(key, "bwd_warps")) { g_bwd_warps = value; return MSDA_OK; }
     if (!strcmp(key, "force_generic")) { g_force_generic = value; return MSDA_OK; }
     if (!strcmp(key, "force_linear_walk")) { g_force_linear = value; return MSDA_OK; }
+#ifdef MSDA_EXPERIMENTS
+    if (!strcmp(key, "bwd_mode")) { g_bwd_mode = value; return MSDA_OK; }
     if (!strcmp(key, "debug_skip_scatter")) { g_skip_scatter = value; return MSDA_OK; }
+#else
+    if (!strcmp(key, "bwd_mode") || !strcmp(key, "debug_skip_scatter"))
+        return fail(MSDA_ERR_UNSUPPORTED, "msda_set_option: measurement-only switch, compiled in with -DMSDA_EXPERIMENTS only (tools/)");
+#endif
     if (!strcmp(key, "bwd_deep")) { g_bwd_deep = value; return MSDA_OK; }
+    if (!strcmp(key, "bwd_algo")) { g_bwd_algo = value; return MSDA_OK; }
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_set_option: unknown key");
 }
 

@@ -253,6 +253,152 @@ def test_bf16_value_vs_oracle(dev):
         assert rel_err(ga, wga) <= BWD_TOL and rel_err(gl[keep], wgl[keep]) <= BWD_TOL
 
 
+def _bf16_check(x, got, eps=1e-4):
+    """bf16 tolerances (DESIGN.md section 6): vs the fp64 oracle on the bf16-ROUNDED value / grad_output;
+    bf16-emitted tensors 2^-8, fp32-emitted gradients the fp32 limits."""
+    from oracle.compare import boundary_mask, rel_err
+    out, gv, gl, ga = got
+    wout, wgv, wgl, wga = oracle64(x)
+    n = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    keep = ~boundary_mask(n(x["loc"]), n(x["shapes"]), eps)
+    errs = dict(out=rel_err(out, wout), grad_value=rel_err(gv, wgv), grad_attn=rel_err(ga, wga), grad_loc=rel_err(gl[keep], wgl[keep]))
+    assert errs["out"] <= 2 ** -8 and errs["grad_value"] <= 2 ** -8, errs
+    assert errs["grad_attn"] <= BWD_TOL and errs["grad_loc"] <= BWD_TOL, errs
+    return errs
+
+
+@pytest.mark.parametrize("regime", ["init", "uniform"])
+@pytest.mark.parametrize("config", ["a2d", "ytvos"])
+def test_full_shapes_vs_oracle_fp32_and_bf16(dev, config, regime):
+    """BASELINE.json configs[1] (A2D, N=5, S=4820) and configs[2] (YTVOS, N=10, S=15300) at FULL size against the
+    C oracle in fp64 -- fp32 at the north_star tolerances, bf16 value at the stated bf16 tolerance."""
+    from ocpg_b200.workloads import A2D_ENCODER, YTVOS_ENCODER, make_inputs
+    wl = A2D_ENCODER if config == "a2d" else YTVOS_ENCODER
+    x = make_inputs(wl, regime, seed=13)
+    want = oracle64(x)
+    errs = check(ours(x, dev), want, x)
+    print(config, regime, "fp32", errs)
+    xb = dict(x)
+    xb["value"] = x["value"].bfloat16().float()
+    xb["grad_out"] = x["grad_out"].bfloat16().float()
+    print(config, regime, "bf16", _bf16_check(xb, ours(xb, dev, torch.float32, value_dtype=torch.bfloat16)))
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("emit", [True, False])
+def test_fused_bf16_vs_oracle(dev, ref_dim, emit):
+    """msda_fused_{forward,backward}_bf16 (bf16 value / output / grad_output, fp32 offsets, logits, reference points)
+    against the fp64 oracle fed the locations / probabilities the fused kernel itself must produce (torch formulation of
+    ms_deform_attn.py:101-110 in fp64 on the same fp32 inputs), with the softmax / offset chain rule applied in fp64."""
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    from ocpg_b200.workloads import encoder_reference_points, encoder_workload
+    from oracle.compare import boundary_mask, rel_err
+    wl = encoder_workload("t", 2, 96, 160)
+    g = torch.Generator().manual_seed(31 + ref_dim)
+    N, S, M, D, L, P, Lq = wl.n_frames, wl.S, 8, 32, wl.L, 4, wl.S
+    shapes = torch.tensor(wl.levels)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, S, M, D, generator=g).bfloat16()
+    gout = torch.randn(N, Lq, M * D, generator=g).bfloat16()
+    offsets = torch.randn(N, Lq, M, L, P, 2, generator=g) * 2.0
+    logits = torch.randn(N, Lq, M, L * P, generator=g) * 2
+    ref2 = encoder_reference_points(wl.levels, "cpu")[None].expand(N, -1, -1, -1).contiguous()
+    refp = ref2 if ref_dim == 2 else torch.cat((ref2, torch.rand(N, Lq, L, 2, generator=g) * 0.3 + 0.05), -1).contiguous()
+    d = lambda t: t.to(dev)
+    args = (d(value), d(shapes), d(start), d(offsets), d(logits), d(refp))
+    out, loc, aw = MSDA.ms_deform_attn_fused_forward(*args, 64, emit)
+    gv, g_off, g_logits, g_loc = MSDA.ms_deform_attn_fused_backward(*args, d(gout), 64, True)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16 and gv.dtype == torch.bfloat16
+    assert (loc is None and aw is None) if not emit else (loc.dtype == torch.float32 and aw.dtype == torch.float32)
+    # the module's arithmetic in torch fp32 (bit-identical locations are checked in test_fused_operator_matches_unfused)
+    aw32 = torch.softmax(logits, -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        wh = torch.stack([shapes[..., 1], shapes[..., 0]], -1).float()
+        loc32 = refp[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        scale = 1.0 / wh[None, None, None, :, None, :].double()
+    else:
+        loc32 = refp[:, :, None, :, None, :2] + offsets / P * refp[:, :, None, :, None, 2:] * 0.5
+        scale = (refp[:, :, None, :, None, 2:].double() * 0.5 / P).expand(N, Lq, M, L, P, 2)
+    if emit:
+        assert torch.equal(loc.cpu(), loc32) and rel_err(aw, aw32) <= 1e-6
+    x = dict(value=value.float(), shapes=shapes, start=start, loc=loc32.contiguous(), attn=aw32.contiguous(), grad_out=gout.float())
+    wout, wgv, wgl, wga = oracle64(x)
+    assert rel_err(out.float(), wout) <= 2 ** -8 and rel_err(gv.float(), wgv) <= 2 ** -8
+    keep = ~boundary_mask(x["loc"].numpy(), shapes.numpy(), 1e-4)
+    f = lambda t: t.double().cpu().numpy()
+    assert rel_err(f(g_loc)[keep], wgl[keep]) <= BWD_TOL
+    assert rel_err(f(g_off)[keep], (wgl * scale.numpy())[keep]) <= BWD_TOL
+    p64 = aw32.double().numpy().reshape(N, Lq, M, L * P)
+    ga64 = wga.reshape(N, Lq, M, L * P)
+    want_logits = p64 * (ga64 - (p64 * ga64).sum(-1, keepdims=True))
+    assert rel_err(f(g_logits), want_logits) <= BWD_TOL
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_more_than_2_31_value_elements(dev, dtype):
+    """SURVEY.md section 7 'index overflow': N*S*M*D > 2^31 in ONE launch (the reference's int indexing, cuh:255-269,
+    overflows there; its wrapper never gets this far only because of the im2col_step chunk loop).  The last and a middle
+    frame of the big launch must equal the same frames run alone."""
+    import ocpg_b200.MultiScaleDeformableAttention as MSDA
+    from ocpg_b200.workloads import A2D_ENCODER, make_inputs
+    import dataclasses
+    free, _ = torch.cuda.mem_get_info()
+    if free < 110 * (1 << 30):
+        pytest.skip("needs ~100 GB of free device memory")
+    N = 1760                                   # 1760 * 4820 * 256 = 2.17e9 > 2^31
+    wl = dataclasses.replace(A2D_ENCODER, n_frames=N)
+    assert N * wl.S * 256 > 2 ** 31
+    vdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    g = torch.Generator(device=dev).manual_seed(17)
+    shapes = torch.tensor(wl.levels, device=dev)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = wl.S
+    value = torch.randn(N, S, 8, 32, device=dev, generator=g, dtype=torch.float32).to(vdt)
+    gout = torch.randn(N, S, 256, device=dev, generator=g, dtype=torch.float32).to(vdt)
+    small = make_inputs(dataclasses.replace(A2D_ENCODER, n_frames=8), "init", seed=3, device=dev)
+    loc = small["loc"].repeat(N // 8, 1, 1, 1, 1, 1).contiguous()
+    attn = small["attn"].repeat(N // 8, 1, 1, 1, 1).contiguous()
+    out = MSDA.ms_deform_attn_forward(value, shapes, start, loc, attn, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(value, shapes, start, loc, attn, gout, 64)
+    torch.cuda.synchronize()
+    for lo, hi in ((N - 2, N), (N // 2 + 3, N // 2 + 5), (0, 1)):
+        sl = slice(lo, hi)
+        o1 = MSDA.ms_deform_attn_forward(value[sl].contiguous(), shapes, start, loc[sl].contiguous(), attn[sl].contiguous(), 64)
+        gv1, gl1, ga1 = MSDA.ms_deform_attn_backward(value[sl].contiguous(), shapes, start, loc[sl].contiguous(),
+                                                     attn[sl].contiguous(), gout[sl].contiguous(), 64)
+        assert torch.equal(out[sl], o1), (lo, hi)
+        assert torch.equal(gl[sl], gl1) and torch.equal(ga[sl], ga1), (lo, hi)
+        tol = 2 ** -7 if dtype == "bf16" else 1e-5          # grad_value: atomics in a different order (+ one bf16 rounding)
+        assert (gv[sl].float() - gv1.float()).abs().max().item() <= tol * gv1.float().abs().max().item(), (lo, hi)
+    # nothing leaked outside: every frame's grad_value is finite and non-trivial
+    assert torch.isfinite(gv[::97].float()).all() and gv[N - 1].float().abs().max().item() > 0
+
+
+def test_measurement_switches_are_not_in_the_product_build(dev):
+    """bwd_mode / debug_skip_scatter return wrong gradients by design: they exist only in -DMSDA_EXPERIMENTS builds."""
+    import ocpg_b200
+    for key in ("bwd_mode", "debug_skip_scatter"):
+        with pytest.raises(RuntimeError, match="MSDA_EXPERIMENTS"):
+            ocpg_b200.set_option(key, 1)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_backward_algorithms_agree(dev, algo):
+    """bwd_algo 0 (row-major msda_bwd_sorted, the default) and 1 (query-major msda_bwd_tiled) against the oracle on a shape
+    with ragged tiles, in both regimes, plus windows that overflow (sigma = 12 px) and near-total row sharing (0.3 px)."""
+    import ocpg_b200
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 3, 104, 184)          # levels 13x23, 7x12, 4x6, 2x3: no dimension a multiple of the tile
+    ocpg_b200.set_option("bwd_algo", algo)
+    try:
+        for regime, sigma in (("init", 2.0), ("init", 12.0), ("uniform", 2.0), ("init", 0.3)):
+            x = make_inputs(wl, regime, seed=19, sigma_px=sigma)
+            check(ours(x, dev), oracle64(x), x)
+    finally:
+        ocpg_b200.set_option("bwd_algo", 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference's own CUDA op, rebuilt for sm_100a (oracle/_ref)
 # ------------------------------------------------------------------------------------------------
