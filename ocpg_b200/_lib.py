@@ -63,6 +63,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def source_fingerprint() -> str:
+    """First 16 hex digits of the SHA-256 of the kernel sources (csrc/*, include/msda_sm100.h): ties profiles (ncu
+    captures, profiles/traffic.json) to the kernels they were taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(_PKG, "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join(INCLUDE, "msda_sm100.h")]:
+        path = f if os.path.isabs(f) else os.path.join(csrc, f)
+        if path.endswith((".cu", ".cuh", ".h")):
+            with open(path, "rb") as fh:
+                h.update(os.path.basename(path).encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def lib() -> ctypes.CDLL:
     """The loaded library; raises RuntimeError (never falls back) if it is not there."""
     global _lib

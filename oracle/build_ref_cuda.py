@@ -5,8 +5,8 @@ cpu/ms_deform_attn_cpu.cpp, cuda/ms_deform_attn_cuda.cu); nothing is copied into
 accommodation for torch 2.11 is the force-included oracle/ref_compat.h (see there).  Output:
 oracle/_ref/MultiScaleDeformableAttention_ref.so, a torch extension exposing the reference's
 ms_deform_attn_forward / ms_deform_attn_backward (vision.cpp:13-16).  It is git-ignored but travels to
-the GPU box, where tests/test_parity_gpu.py uses it as the second oracle and bench_ref_cuda.py as the
-"kernel to beat".  It cannot run here (no GPU) and /root/reference does not exist on the GPU box, so
+the GPU box, where tests/test_parity_gpu.py uses it as the second oracle and bench.py's `gpu_baseline` leg
+(time_reference_cuda_op) times it as the "kernel to beat".  It cannot run here (no GPU) and /root/reference does not exist on the GPU box, so
 build here, load there.
 """
 from __future__ import annotations
