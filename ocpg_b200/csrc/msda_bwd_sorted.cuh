@@ -53,10 +53,18 @@ template <int ROUNDS> struct SortSmem {
     uint32_t n_runs, n_win_loose, n_overflow, pad_;
     alignas(16) uint2 hist[kSortCells];                          // per window cell: {items, runs before | loose items before << 16}
     uint32_t rows[kItems];                                       // row (unit offset) of run r at [r], of loose item i at [kItems-1-i]
-    uint2 items[kSlots + 4];                                     // {grad_out row offset | p slot << 16, a * w_corner}
+    alignas(16) uint2 items[kSlots + 4];                                     // {grad_out row offset | p slot << 16, a * w_corner}
     float4 go[kQueries][8];                                      // grad_out rows of the tile's queries, fp32
     float4 p[kQueries * kPoints + 1];                            // per (query, point): the four corner dot products (+ dummy)
 };
+
+// -DMSDA_CHECKED (tools/ builds only): every shared-memory index the sort derives from data is range-checked and the
+// kernel traps on a violation -- compute-sanitizer is closed on the B200 pool (profiles/r2_compute_sanitizer_closed.log).
+#ifdef MSDA_CHECKED
+#define SORT_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define SORT_CHECK(cond) do { } while (0)
+#endif
 
 #ifndef MSDA_SORT_MINB
 #define MSDA_SORT_MINB 4      // resident CTAs per SM the register budget is set for (4 -> 64 registers; ~55 KB of shared memory each)
@@ -189,14 +197,21 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
         __syncthreads();                                                                        // S1: statistics complete
 
         // ---- histogram: window origin per level, cell of each valid corner, rank inside the cell ----
-        int ox[ROUNDS], oy[ROUNDS];
-        uint32_t rank[ROUNDS][2];      // four 16-bit ranks per round
+        // Kept per round for the later phases: cell00 = window cell of the top-left corner (the others are +1, +kWinX,
+        // +kWinX+1), mask = corners inside the window (bits 0-3) | valid corners outside it (bits 4-7), four 16-bit ranks.
+        int cell00[ROUNDS];
+        uint32_t mask[ROUNDS], rank[ROUNDS][2];
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int l = sp[r].level;
             const int4 st = *reinterpret_cast<const int4 *>(sm.stat[l]);
-            ox[r] = window_origin(st.x, st.z, kWinX, lt.W[l]);
-            oy[r] = window_origin(st.y, st.z, kWinY, lt.H[l]);
+            const int ux = sp[r].x0 - window_origin(st.x, st.z, kWinX, lt.W[l]);
+            const int uy = sp[r].y0 - window_origin(st.y, st.z, kWinY, lt.H[l]);
+            cell00[r] = l * kWinCells + uy * kWinX + ux;
+            const uint32_t in_x = ((unsigned)ux < (unsigned)kWinX ? 5u : 0u) | ((unsigned)(ux + 1) < (unsigned)kWinX ? 10u : 0u);
+            const uint32_t in_y = ((unsigned)uy < (unsigned)kWinY ? 3u : 0u) | ((unsigned)(uy + 1) < (unsigned)kWinY ? 12u : 0u);
+            const uint32_t inw = in_x & in_y & (uint32_t)sp[r].valid;
+            mask[r] = inw | (((uint32_t)sp[r].valid & ~inw) << 4);
         }
         if (tid < d.L) {      // the same origins, published for the scan
             const int4 st = *reinterpret_cast<const int4 *>(sm.stat[tid]);
@@ -205,25 +220,22 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
         }
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
-            const int cbase = sp[r].level * kWinCells;
-            rank[r][0] = rank[r][1] = 0;
+            // items outside their window: one ticket per thread and round (rare in the encoder's regimes)
+            const uint32_t n_out = __popc(mask[r] >> 4);
+            uint32_t out_rank = 0;
+            if (n_out) out_rank = atomicAdd(&sm.n_overflow, n_out);
+            uint32_t rk[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const bool cv = (sp[r].valid >> c) & 1;
-                const int ux = sp[r].x0 + (c & 1) - ox[r], uy = sp[r].y0 + (c >> 1) - oy[r];
-                const bool inw = cv && (unsigned)ux < (unsigned)kWinX && (unsigned)uy < (unsigned)kWinY;
-                uint32_t rk = 0;
-                if (inw) rk = atomicAdd(&sm.hist[cbase + uy * kWinX + ux].x, 1u);
-                const bool ovf = cv && !inw;
-                const uint32_t bal = __ballot_sync(kFull, ovf);
-                if (bal) {      // warp-aggregated ticket for the items outside their window
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.n_overflow, (uint32_t)__popc(bal));
-                    base = __shfl_sync(kFull, base, 0);
-                    if (ovf) rk = base + __popc(bal & ((1u << lane) - 1u));
+                rk[c] = out_rank;
+                if ((mask[r] >> (4 + c)) & 1u) ++out_rank;
+                if ((mask[r] >> c) & 1u) {
+                    SORT_CHECK((unsigned)(cell00[r] + (c & 1) + (c >> 1) * kWinX) < (unsigned)kSortCells);
+                    rk[c] = atomicAdd(&sm.hist[cell00[r] + (c & 1) + (c >> 1) * kWinX].x, 1u);
                 }
-                rank[r][c >> 1] |= rk << (16 * (c & 1));
             }
+            rank[r][0] = rk[0] | (rk[1] << 16);
+            rank[r][1] = rk[2] | (rk[3] << 16);
         }
         __syncthreads();                                                                        // S2: histogram complete
 
@@ -272,39 +284,32 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int l = sp[r].level;
-            const int cbase = l * kWinCells;
             const float hx = 1.f - sp[r].lx, hy = 1.f - sp[r].ly;
-            const float w4[4] = {hy * hx, hy * sp[r].lx, sp[r].ly * hx, sp[r].ly * sp[r].lx};
+            const float aw4[4] = {sp[r].aa * (hy * hx), sp[r].aa * (hy * sp[r].lx), sp[r].aa * (sp[r].ly * hx), sp[r].aa * (sp[r].ly * sp[r].lx)};
             const uint32_t tag0 = (uint32_t)(qloc * 128) | ((uint32_t)((qloc * SM::kPoints + 8 * r + cl) * 4) << 16);
-            const int pixel00 = lt.start[l] + sp[r].y0 * lt.W[l] + sp[r].x0;
+            const int row_step = lt.W[l] * pixel_units;
+            const uint32_t unit00 = (uint32_t)((lt.start[l] + sp[r].y0 * lt.W[l] + sp[r].x0) * pixel_units);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (!((sp[r].valid >> c) & 1)) continue;
-                const int ux = sp[r].x0 + (c & 1) - ox[r], uy = sp[r].y0 + (c >> 1) - oy[r];
-                const bool inw = (unsigned)ux < (unsigned)kWinX && (unsigned)uy < (unsigned)kWinY;
+                const bool inw = (mask[r] >> c) & 1u, out = (mask[r] >> (4 + c)) & 1u;
                 const uint32_t rk = (rank[r][c >> 1] >> (16 * (c & 1))) & 0xffffu;
-                const uint32_t unit = (uint32_t)((pixel00 + (c & 1) + (c >> 1) * lt.W[l]) * pixel_units);
-                uint32_t li = n_win_loose + rk;      // loose index (items outside the window come after the window's)
-                uint32_t pos;
-                bool loose = true;
-                if (inw) {
-                    const uint2 h = sm.hist[cbase + uy * kWinX + ux];      // {items of the cell, runs before | loose before << 16}
-                    const uint32_t rem = h.x & 3u;
-                    const uint32_t run_items = rem == 3u ? h.x : h.x - rem;
-                    loose = rk >= run_items;
-                    li = (h.y >> 16) + rk - run_items;
-                    if (!loose) {
-                        const uint32_t run0 = h.y & 0xffffu;
-                        pos = 4 * run0 + rk;
-                        if (!(rk & 3u)) sm.rows[run0 + (rk >> 2)] = unit;
-                        if (rem == 3u && rk + 1 == h.x) sm.items[pos + 1] = make_uint2(SM::kDummySlot << 16, 0u);      // null item pads the run
-                    }
+                const uint32_t unit = unit00 + (uint32_t)((c & 1) * pixel_units + (c >> 1) * row_step);
+                uint2 h = make_uint2(0u, 0u);      // {items of the cell, runs before | loose before << 16}
+                if (inw) h = sm.hist[cell00[r] + (c & 1) + (c >> 1) * kWinX];
+                const uint32_t rem = h.x & 3u;
+                const uint32_t run_items = rem == 3u ? h.x : h.x - rem;      // the first run_items ranks of the cell go to runs
+                const bool in_run = rk < run_items;                           // false outside the window (run_items = 0)
+                const uint32_t li = inw ? (h.y >> 16) + rk - run_items : n_win_loose + rk;
+                const uint32_t pos = in_run ? 4u * (h.y & 0xffffu) + rk : (uint32_t)(SM::kSlots - 1) - li;
+                const uint32_t row_at_ = in_run ? (h.y & 0xffffu) + (rk >> 2) : (uint32_t)(SM::kItems - 1) - li;
+                if (inw || out) {
+                    SORT_CHECK(pos < (uint32_t)SM::kSlots && row_at_ < (uint32_t)SM::kItems && (!inw || rk < h.x));
+                    SORT_CHECK(!in_run || (pos < 4u * (uint32_t)n_runs && row_at_ < (uint32_t)n_runs));
+                    SORT_CHECK(in_run || (li < (uint32_t)n_loose && 4u * (uint32_t)n_runs + li < (uint32_t)SM::kSlots));
+                    sm.items[pos] = make_uint2(tag0 + ((uint32_t)c << 16), __float_as_uint(aw4[c]));
+                    if (!in_run || !(rk & 3u)) sm.rows[row_at_] = unit;
+                    if (in_run && rem == 3u && rk + 1 == h.x) sm.items[pos + 1] = make_uint2(SM::kDummySlot << 16, 0u);      // null item pads the run
                 }
-                if (loose) {
-                    pos = SM::kSlots - 1 - li;
-                    sm.rows[SM::kItems - 1 - li] = unit;
-                }
-                sm.items[pos] = make_uint2(tag0 + ((uint32_t)c << 16), __float_as_uint(sp[r].aa * w4[c]));
             }
         }
         __syncthreads();                                                                        // S5: items complete
@@ -325,34 +330,41 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                 int run = warp * 4 + grp;
                 bool has = run < n_runs;
                 uint32_t unit = has ? sm.rows[run] : 0u;
-                const uint2 *ip = &sm.items[has ? 4 * run : SM::kSlots];
-                Row v = IO::load(row_at(vb, unit));
+                const uint4 *ip = reinterpret_cast<const uint4 *>(&sm.items[has ? 4 * run : SM::kSlots]);
+                Row v = IO::load_stream(row_at(vb, unit));
+                const bool up4 = (cl & 4) != 0, up2 = (cl & 2) != 0, even = !(cl & 1);
 #pragma unroll 2
                 for (int base = warp * 4; base < n_runs; base += 32) {
                     run += 32;
                     const bool has_next = run < n_runs;
                     const uint32_t unit_next = has_next ? sm.rows[run] : 0u;
-                    const uint2 *ip_next = &sm.items[has_next ? 4 * run : SM::kSlots];
-                    const Row v_next = IO::load(row_at(vb, unit_next));      // next row in flight during this run
+                    const uint4 *ip_next = reinterpret_cast<const uint4 *>(&sm.items[has_next ? 4 * run : SM::kSlots]);
+                    const Row v_next = IO::load_stream(row_at(vb, unit_next));      // next row in flight during this run
+                    const uint4 i01 = ip[0], i23 = ip[1];                            // {tag, a*w} of items 0,1 and 2,3
+                    const uint32_t tag[4] = {i01.x, i01.z, i23.x, i23.z};
+                    SORT_CHECK((tag[0] & 0xffffu) < 4096u && (tag[3] & 0xffffu) < 4096u && (tag[0] >> 16) <= SM::kDummySlot && (tag[3] >> 16) <= SM::kDummySlot);
+                    const float aw[4] = {__uint_as_float(i01.y), __uint_as_float(i01.w), __uint_as_float(i23.y), __uint_as_float(i23.w)};
                     Row acc{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
                     float ds[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint2 it = ip[k];
-                        const Row g = go_row(it.x);
-                        fma_row(__uint_as_float(it.y), g, acc);      // grad_value[row] += (a * w_corner) * grad_out   (cuh:125,134,143,152)
-                        ds[k] = dot_row(g, v);                       // this lane's four channels of <grad_out, value row>
+                        const Row g = go_row(tag[k]);
+                        fma_row(aw[k], g, acc);          // grad_value[row] += (a * w_corner) * grad_out   (cuh:125,134,143,152)
+                        ds[k] = dot_row(g, v);           // this lane's four channels of <grad_out, value row>
                     }
                     // reduce over the 8 lanes of the group: lanes 2j, 2j+1 end with the sum of item j
-                    const bool up4 = (cl & 4) != 0, up2 = (cl & 2) != 0;
                     const float e0 = (up4 ? ds[2] : ds[0]) + __shfl_xor_sync(kFull, up4 ? ds[0] : ds[2], 4);
                     const float e1 = (up4 ? ds[3] : ds[1]) + __shfl_xor_sync(kFull, up4 ? ds[1] : ds[3], 4);
                     float tot = (up2 ? e1 : e0) + __shfl_xor_sync(kFull, up2 ? e0 : e1, 2);
                     tot += __shfl_xor_sync(kFull, tot, 1);
-                    if (!(cl & 1)) p_flat[ip[cl >> 1].x >> 16] = tot;      // null items: the dummy slot
-                    if (has)
-                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
-                                     :: "l"(row_at(gb, unit)), "f"(acc.lo.x), "f"(acc.lo.y), "f"(acc.hi.x), "f"(acc.hi.y) : "memory");
+                    const uint32_t my_tag = up4 ? (up2 ? tag[3] : tag[2]) : (up2 ? tag[1] : tag[0]);
+                    if (even) p_flat[my_tag >> 16] = tot;      // null items: the dummy slot
+                    {
+                        const float4 *dst = row_at(gb, unit);
+                        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+                                     "@q red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                                     :: "l"(dst), "f"(acc.lo.x), "f"(acc.lo.y), "f"(acc.hi.x), "f"(acc.hi.y), "r"((uint32_t)has) : "memory");
+                    }
                     has = has_next; unit = unit_next; ip = ip_next; v = v_next;
                 }
             }
@@ -368,7 +380,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                     has[u] = li < n_loose;
                     it[u] = sm.items[has[u] ? SM::kSlots - 1 - li : SM::kSlots];
                     unit[u] = has[u] ? sm.rows[SM::kItems - 1 - li] : 0u;
-                    v[u] = IO::load(row_at(vb, unit[u]));
+                    v[u] = IO::load_stream(row_at(vb, unit[u]));
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
