@@ -10,6 +10,7 @@ A drop-in for the reference's ``models/ops`` package and, 
 Python/PyTorch host code calls hand-written CUDA kernels through the C ABI of include/msda_sm100.h
 (ctypes); no Triton, no multi-backend dispatch, no CPU fallback.
 """
+from ._strict import set_strict, is_strict, fallback_counts  # noqa: F401
 from ._lib import build, lib, launch_count, set_option, source_fingerprint, LIB_PATH  # noqa: F401
 from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction  # noqa: F401
 from .modules import MSDeformAttn  # noqa: F401

@@ -397,7 +397,10 @@ template <int ROUNDS, int WARPS> struct FwdSmem {
 extern __shared__ __align__(16) unsigned char msda_smem[];
 
 template <typename VT, int ROUNDS, int WARPS, bool FUSED>
-__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
+#ifndef MSDA_FWD_WARPS_PER_SM
+#define MSDA_FWD_WARPS_PER_SM 32      // resident forward warps per SM the register budget is set for (32 -> 64 registers)
+#endif
+__global__ void __launch_bounds__(WARPS * 32, MSDA_FWD_WARPS_PER_SM / WARPS)
 msda_fwd_tiled(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ start,
                const float *__restrict__ loc, const float *__restrict__ attn, VT *__restrict__ out, Dims d, FusedArgs fa) {
     using IO = RowIO<VT>;
@@ -909,7 +912,7 @@ template <typename VT, int ROUNDS, int WARPS>
 int launch_fwd_one(const VT *value, const int64_t *shapes, const int64_t *start, const float *loc, const float *attn,
                    VT *out, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
     const size_t smem = sizeof(FwdSmem<ROUNDS, WARPS>);
-    const int grid = grid_for(32 / WARPS, g_fwd_ctas_per_sm);
+    const int grid = grid_for(MSDA_FWD_WARPS_PER_SM / WARPS, g_fwd_ctas_per_sm);
     if (fa) {
         if (const int rc = configure(msda_fwd_tiled<VT, ROUNDS, WARPS, true>, smem)) return rc;
         msda_fwd_tiled<VT, ROUNDS, WARPS, true><<<grid, WARPS * 32, smem, st>>>(value, shapes, start, loc, attn, out, d, *fa);

@@ -24,7 +24,7 @@ from torch import nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import _lib, epilogue
+from . import _lib, _strict, epilogue
 from .encoder import _activation
 from .modules import MSDeformAttn
 
@@ -66,6 +66,7 @@ def scale_reference_points(reference_points: torch.Tensor, valid_ratios: torch.T
         raise AssertionError("reference_points must have 2 or 4 coordinates")                       # :362
     if _native_ok(reference_points, valid_ratios):
         return _ScaleReferencePoints.apply(reference_points, valid_ratios)
+    _strict.note_fallback("scale_reference_points", "needs fp32 CUDA tensors outside autocast")
     scale = valid_ratios if reference_points.shape[-1] == 2 else torch.cat([valid_ratios, valid_ratios], -1)
     return reference_points[:, :, None] * scale[:, None]
 
@@ -107,6 +108,7 @@ def select_top_samples(sampling_locations, attention_weights, valid_ratios, top:
     K = M * L * P
     if _native_ok(sampling_locations, attention_weights, valid_ratios) and top <= 32 and top <= K <= 256:
         return _SelectTopSamples.apply(sampling_locations, attention_weights, valid_ratios, top)
+    _strict.note_fallback("select_top_samples", "needs fp32 CUDA tensors outside autocast, top <= 32 and top <= M*L*P <= 256")
     loc = sampling_locations / valid_ratios[:, None, None, :, None, :]
     weights, idx = attention_weights.reshape(N, Lq, -1).topk(top, dim=2)
     keep = torch.gather(loc.reshape(N, Lq, -1, 2), 2, idx.unsqueeze(-1).repeat(1, 1, 1, 2))
@@ -149,6 +151,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
         q = k = self.with_pos_embed(tgt, query_pos)
         tgt2 = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), tgt.transpose(0, 1))[0].transpose(0, 1)          # :326
         if not self._epilogue_ok(tgt):
+            if self.fused:
+                _strict.note_fallback("DeformableTransformerDecoderLayer epilogue", "needs ReLU, dropout in [0, 1), fp32 CUDA, d_model in %r" % (epilogue.LN_CHANNELS,))
             tgt = self.norm2(tgt + self.dropout2(tgt2))
             with torch.autocast(device_type=tgt.device.type, enabled=False):
                 tgt2, sampling_locations, attention_weights = self.cross_attn(

@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import epilogue
+from . import epilogue, _strict
 from ._shapes import remember_host_shapes, shapes_on_host as _shapes_on_host  # noqa: F401
 from .modules import MSDeformAttn
 
@@ -81,6 +81,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
             hidden = epilogue.linear_relu(src, self.linear1.weight, self.linear1.bias, rng, 2, p2)           # :244
             return epilogue.bias_residual_layer_norm(F.linear(hidden, self.linear2.weight), self.linear2.bias, src,
                                                      self.norm2.weight, self.norm2.bias, self.norm2.eps, rng, 3, p3)   # :245-247
+        if self.fused:
+            _strict.note_fallback("DeformableTransformerEncoderLayer epilogue",
+                                  "needs ReLU, dropout in [0, 1), fp32 CUDA, d_model in %r" % (epilogue.LN_CHANNELS,))
         with torch.autocast(device_type=src.device.type, enabled=False):
             attn_out = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                                       level_start_index, padding_mask)[0]

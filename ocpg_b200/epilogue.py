@@ -26,7 +26,7 @@ import torch.nn.functional as F
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import _lib
+from . import _lib, _strict
 
 LN_CHANNELS = (128, 256, 512, 1024)
 
@@ -128,6 +128,7 @@ def bias_residual_layer_norm(x, bias, residual, gamma, beta, eps=1e-5, rng=None,
     ``p > 0``; ``salt`` names the call site."""
     if supported(x, bias, residual, gamma, beta) and x.shape[-1] in LN_CHANNELS and x.shape == residual.shape:
         return _BiasResidualLayerNorm.apply(x, bias, residual, gamma, beta, eps, rng, salt, p)
+    _strict.note_fallback("bias_residual_layer_norm", "needs fp32 CUDA tensors outside autocast, channels in %r, x.shape == residual.shape" % (LN_CHANNELS,))
     y = x if bias is None else x + bias
     if rng is not None and p > 0.0:
         y = F.dropout(y, p, True)
@@ -156,6 +157,7 @@ class _Linear(Function):
 def linear(x, weight, bias):
     if bias is not None and supported(x, weight, bias) and weight.shape[0] % 4 == 0:
         return _Linear.apply(x, weight, bias)
+    _strict.note_fallback("linear", "needs a bias, fp32 CUDA tensors outside autocast and out_features % 4 == 0")
     return F.linear(x, weight, bias)
 
 
@@ -204,5 +206,6 @@ def linear_relu(x, weight, bias, rng=None, salt=0, p=0.0):
     """``dropout(relu(F.linear(x, weight, bias)))`` (dropout when ``rng`` is given and ``p > 0``)."""
     if bias is not None and supported(x, weight, bias) and weight.shape[0] % 4 == 0:
         return _LinearReLU.apply(x, weight, bias, rng, salt, p)
+    _strict.note_fallback("linear_relu", "needs a bias, fp32 CUDA tensors outside autocast and out_features % 4 == 0")
     h = F.relu(F.linear(x, weight, bias))
     return F.dropout(h, p, True) if rng is not None and p > 0.0 else h

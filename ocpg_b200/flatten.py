@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import _lib
+from . import _lib, _strict
 
 MAX_LEVELS = 8
 
@@ -123,6 +123,7 @@ def flatten_levels(srcs: List[torch.Tensor], pos_embeds: Optional[List[torch.Ten
                                    *srcs, *(pos_embeds or []))
         src_flat, pos_flat = out if pos_embeds is not None else (out, None)
         return src_flat, pos_flat, spatial_shapes, level_start_index
+    _strict.note_fallback("flatten_levels", "needs fp32 CUDA maps outside autocast")
     src_flat = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
     pos_flat = None
     if pos_embeds is not None:
@@ -155,6 +156,7 @@ def unflatten_levels(memory: torch.Tensor, shapes: Sequence[Tuple[int, int]]) ->
     shapes = [(int(h), int(w)) for h, w in shapes]
     if _native_ok([memory]) and 0 < len(shapes) <= MAX_LEVELS:
         return list(_UnflattenLevels.apply(memory, tuple(shapes)))
+    _strict.note_fallback("unflatten_levels", "needs an fp32 CUDA tensor outside autocast and 1..%d levels" % MAX_LEVELS)
     out, at = [], 0
     N, _, C = memory.shape
     for h, w in shapes:

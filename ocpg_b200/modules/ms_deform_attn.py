@@ -130,9 +130,11 @@ class MSDeformAttn(nn.Module):
                 reference_points.shape[-1]))
         if self.fused and value.is_cuda and MSDA.fused_supported(value, L, P):
             logits = lin(self.attention_weights, query).view(N, Len_q, M, L * P)
+            # the fused kernels take fp32 offsets / logits / reference points whatever the dtype of `value` (a bf16 module
+            # produces bf16 ones): the casts keep the gradient flowing back in the module's dtype
             return MSDeformAttnFusedFunction.apply(
-                value.contiguous(), input_spatial_shapes, input_level_start_index, offsets.contiguous(),
-                logits.contiguous(), reference_points.to(torch.float32).contiguous(), self.im2col_step, self.emit_sampling)
+                value.contiguous(), input_spatial_shapes, input_level_start_index, offsets.float().contiguous(),
+                logits.float().contiguous(), reference_points.to(torch.float32).contiguous(), self.im2col_step, self.emit_sampling)
         weights = F.softmax(lin(self.attention_weights, query).view(N, Len_q, M, L * P), -1)  # :101-102
         weights = weights.view(N, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:                                              # :104-107

@@ -263,3 +263,28 @@ def test_side_kernel_argument_errors_do_not_touch_the_gpu():
     assert L.msda_unflatten_levels_f32(2, one, hw, hw, 1, 8, 10, ptrs, None) == INVALID                               # spatial_size < pixels
     odd = (ctypes.c_void_p * 2)(one + 4, one)
     assert L.msda_unflatten_levels_f32(2, one, hw, hw, 1, 8, 0, odd, None) == INVALID                                 # 16-byte kernels need alignment
+
+
+def test_strict_mode_raises_instead_of_falling_back_to_torch():
+    """The helpers around the operator run a torch formulation for layouts their kernels do not cover (here: CPU
+    tensors); in strict mode that is an error, so a benchmark cannot measure torch by accident."""
+    import torch
+    import ocpg_b200
+    from ocpg_b200 import decoder, epilogue, flatten
+    x, w, b = torch.randn(6, 256), torch.randn(8, 256), torch.randn(8)
+    before = ocpg_b200.fallback_counts().get("linear", 0)
+    assert epilogue.linear(x, w, b).shape == (6, 8)
+    assert ocpg_b200.fallback_counts()["linear"] == before + 1
+    ocpg_b200.set_strict(True)
+    try:
+        assert ocpg_b200.is_strict()
+        for call in (lambda: epilogue.linear(x, w, b), lambda: epilogue.linear_relu(x, w, b),
+                     lambda: epilogue.bias_residual_layer_norm(x, None, x, torch.ones(256), torch.zeros(256)),
+                     lambda: flatten.flatten_levels([torch.randn(1, 4, 2, 2)]),
+                     lambda: flatten.unflatten_levels(torch.randn(1, 4, 4), [(2, 2)]),
+                     lambda: decoder.scale_reference_points(torch.rand(1, 2, 2), torch.rand(1, 4, 2)),
+                     lambda: decoder.select_top_samples(torch.rand(1, 2, 8, 4, 4, 2), torch.rand(1, 2, 8, 4, 4), torch.rand(1, 4, 2))):
+            with pytest.raises(RuntimeError, match="strict mode"):
+                call()
+    finally:
+        ocpg_b200.set_strict(False)

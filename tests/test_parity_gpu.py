@@ -581,6 +581,37 @@ def test_fused_operator_matches_unfused(dev, ref_dim, regime):
     assert loc3 is None and aw3 is None and torch.equal(out3, out1.detach())
 
 
+def test_bf16_module_takes_the_fused_path(dev):
+    """A bf16 MSDeformAttn (bf16 Linears -> bf16 offsets / logits) reaches msda_fused_*_bf16 instead of raising, and agrees
+    with the fp32 module on the same weights within bf16 resolution; strict mode proves no helper fell back to torch."""
+    import ocpg_b200
+    from ocpg_b200 import MSDeformAttn
+    from oracle.compare import rel_err
+    torch.manual_seed(0)
+    m32 = MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():
+        m32.sampling_offsets.weight.normal_(0, 0.02)
+        m32.attention_weights.weight.normal_(0, 0.05)
+    m16 = copy.deepcopy(m32).bfloat16()
+    m32.fused = m16.fused = True
+    shapes = torch.tensor([(12, 20), (6, 10), (3, 5), (2, 3)], device=dev)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    src, query, refp = torch.randn(2, S, 256, device=dev), torch.randn(2, S, 256, device=dev), torch.rand(2, S, 4, 2, device=dev)
+    ocpg_b200.set_strict(True)
+    try:
+        n0 = ocpg_b200.launch_count()
+        s16 = src.bfloat16().requires_grad_(True)
+        out16, loc16, aw16 = m16(query.bfloat16(), refp, s16, shapes, start)
+        out16.float().sum().backward()
+        assert ocpg_b200.launch_count() - n0 >= 2
+    finally:
+        ocpg_b200.set_strict(False)
+    out32, loc32, aw32 = m32(query, refp, src, shapes, start)
+    assert out16.dtype == torch.bfloat16 and s16.grad is not None and torch.isfinite(s16.grad.float()).all()
+    assert rel_err(out16.float(), out32) <= 3e-2 and rel_err(loc16, loc32) <= 2e-2 and rel_err(aw16, aw32) <= 3e-2
+
+
 def test_fused_rejects_unsupported_layouts(dev):
     import ocpg_b200.MultiScaleDeformableAttention as MSDA
     v = torch.randn(1, 6, 2, 16, device=dev)                     # 16 channels per head: generic kernels only
