@@ -72,6 +72,17 @@ def _dtype_suffix(value, sampling_loc, attn_weight):
     return sfx
 
 
+# bf16 value: how grad_value is accumulated.  False (default): fp32 buffer + one conversion pass (error of ONE bf16
+# rounding, the tolerance the tests state).  True: packed bf16 reds straight into the bf16 grad_value (half the L2 atomic
+# sectors, no buffer, no conversion pass; every red rounds the running sum -- see DESIGN.md for the measured error).
+BF16_GRAD_VALUE_DIRECT = False
+
+
+def set_bf16_grad_value_direct(on: bool) -> None:
+    global BF16_GRAD_VALUE_DIRECT
+    BF16_GRAD_VALUE_DIRECT = bool(on)
+
+
 def _stream(device) -> int:
     return _lib.raw_stream(device)                                               # cu:65: current stream
 
@@ -151,12 +162,13 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         st = _stream(value.device)
         L_ = _lib.lib()
         if sfx == "bf16":
-            acc = torch.empty(value.shape, dtype=torch.float32, device=value.device)   # zero-filled by the call
+            direct = BF16_GRAD_VALUE_DIRECT and L <= 4
+            acc = None if direct else torch.empty(value.shape, dtype=torch.float32, device=value.device)   # zero-filled by the call
             grad_value = torch.empty_like(value)
             rc = L_.msda_backward_bf16(
                 grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                 sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
-                acc.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), st)
+                None if direct else acc.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), st)
         else:
             grad_value = torch.empty_like(value)                                       # zero-filled by the call
             rc = getattr(L_, f"msda_backward_{sfx}")(
@@ -242,8 +254,9 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, offs
                   offsets.data_ptr(), logits.data_ptr(), reference_points.data_ptr(), ref_dim, N, S, M, D, L, Lq, P)
         grad_value = torch.empty_like(value)
         if sfx == "bf16":
-            acc = torch.empty(value.shape, dtype=torch.float32, device=value.device)
-            rc = L_.msda_fused_backward_bf16(*common, acc.data_ptr(), grad_value.data_ptr(), g_off.data_ptr(),
+            direct = BF16_GRAD_VALUE_DIRECT and L <= 4
+            acc = None if direct else torch.empty(value.shape, dtype=torch.float32, device=value.device)
+            rc = L_.msda_fused_backward_bf16(*common, None if direct else acc.data_ptr(), grad_value.data_ptr(), g_off.data_ptr(),
                                              g_logits.data_ptr(), g_loc_ptr, st)
         else:
             rc = L_.msda_fused_backward_f32(*common, grad_value.data_ptr(), g_off.data_ptr(), g_logits.data_ptr(),

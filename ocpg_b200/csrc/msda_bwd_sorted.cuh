@@ -104,15 +104,35 @@ __device__ __forceinline__ int window_origin(int sum, int cnt, int win, int size
     return max(min(mean - win / 2 + 1, size - win), 0);
 }
 
-template <typename VT, int ROUNDS, bool FUSED>
+// grad_value row (this lane's four channels) += r: one vector red.  GV16 = false: the fp32 tensor / accumulation buffer
+// (REDG.E.ADD.F32x4); GV16 = true: straight into a bf16 grad_value as packed pairs (REDG.E.ADD.BF16x4: half the L2 atomic
+// sectors, no fp32 buffer, no conversion pass -- but every red rounds the running sum in memory to bf16).
+template <bool GV16>
+__device__ __forceinline__ void red_run(void *slice_base, uint32_t unit, const Row &r, bool on) {
+    if constexpr (!GV16) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+                     "@q red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                     :: "l"(row_at(static_cast<float4 *>(slice_base), unit)), "f"(r.lo.x), "f"(r.lo.y), "f"(r.hi.x), "f"(r.hi.y),
+                        "r"((uint32_t)on) : "memory");
+    } else {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(r.lo.x, r.lo.y), hi = __floats2bfloat162_rn(r.hi.x, r.hi.y);
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t"
+                     "@q red.relaxed.gpu.global.add.noftz.v2.bf16x2 [%0], {%1,%2};\n\t}"
+                     :: "l"(row_at(static_cast<uint2 *>(slice_base), unit)), "r"(*reinterpret_cast<const uint32_t *>(&lo)),
+                        "r"(*reinterpret_cast<const uint32_t *>(&hi)), "r"((uint32_t)on) : "memory");
+    }
+}
+
+template <typename VT, int ROUNDS, bool FUSED, bool GV16 = false>
 __global__ void __launch_bounds__(256, MSDA_SORT_MINB)
 msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int64_t *__restrict__ start, const float *__restrict__ loc, const float *__restrict__ attn,
-                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d,
+                void *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn, Dims d,
                 FusedArgs fa) {
     using IO = RowIO<VT>;
     using Vec = typename IO::Vec;
     using SM = SortSmem<ROUNDS>;
+    using GVec = typename std::conditional<GV16, uint2, float4>::type;      // one lane's four channels of a grad_value row
     constexpr int WARPS = 8;
     constexpr int kTaskQueries = Tile<WARPS>::kQueries;
     constexpr uint32_t kFull = 0xffffffffu;
@@ -150,7 +170,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
         const int64_t row = ((int64_t)t.n * d.Lq + max(q, 0)) * d.M + m;
         const int64_t slice = ((int64_t)t.n * d.S * d.M + m) * 8 + cl;      // unit offset of frame n, head m, this lane
         const Vec *vb = reinterpret_cast<const Vec *>(value) + slice;
-        float4 *gb = reinterpret_cast<float4 *>(grad_value) + slice;
+        GVec *gb = static_cast<GVec *>(grad_value) + slice;
 
         // ---- stage: grad_out row -> shared memory, this lane's points -> registers, window statistics ----
         {
@@ -359,12 +379,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                     tot += __shfl_xor_sync(kFull, tot, 1);
                     const uint32_t my_tag = up4 ? (up2 ? tag[3] : tag[2]) : (up2 ? tag[1] : tag[0]);
                     if (even) p_flat[my_tag >> 16] = tot;      // null items: the dummy slot
-                    {
-                        const float4 *dst = row_at(gb, unit);
-                        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
-                                     "@q red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
-                                     :: "l"(dst), "f"(acc.lo.x), "f"(acc.lo.y), "f"(acc.hi.x), "f"(acc.hi.y), "r"((uint32_t)has) : "memory");
-                    }
+                    red_run<GV16>(gb, unit, acc, has);
                     has = has_next; unit = unit_next; ip = ip_next; v = v_next;
                 }
             }
@@ -387,11 +402,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                     const Row g = go_row(it[u].x);
                     const float aw = __uint_as_float(it[u].y);
                     float dsum = dot_row(g, v[u]);
-                    if (has[u]) {
-                        const float2 s0 = __fmul2_rn(splat(aw), g.lo), s1 = __fmul2_rn(splat(aw), g.hi);
-                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
-                                     :: "l"(row_at(gb, unit[u])), "f"(s0.x), "f"(s0.y), "f"(s1.x), "f"(s1.y) : "memory");
-                    }
+                    red_run<GV16>(gb, unit[u], Row{__fmul2_rn(splat(aw), g.lo), __fmul2_rn(splat(aw), g.hi)}, has[u]);
                     // same summation tree as the runs' butterfly (lane pairs 4 apart first): whether an item lands in a run or
                     // here depends on the order of the histogram atomics, and d/d location, d/d attention stay bitwise reproducible
                     dsum += __shfl_xor_sync(kFull, dsum, 4);

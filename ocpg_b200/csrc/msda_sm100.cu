@@ -35,6 +35,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "msda_sm100.h"
 
@@ -964,23 +965,35 @@ int resident_ctas(K kernel, int threads, size_t smem, int fallback) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm <= 0) per_sm = fallback;
     return per_sm;
 }
-template <typename VT, int ROUNDS>
+template <typename VT, int ROUNDS, bool GV16 = false>
 int launch_bwd_sorted(const VT *go, const VT *value, const int64_t *shapes, const int64_t *start, const float *loc,
-                      const float *attn, float *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
+                      const float *attn, void *gv, float *gl, float *ga, const Dims &d, const FusedArgs *fa, cudaStream_t st) {
     const size_t smem = sizeof(SortSmem<ROUNDS>);
     const int knob = g_bwd_ctas_per_sm.load();
     if (fa) {
-        auto kernel = msda_bwd_sorted<VT, ROUNDS, true>;
+        auto kernel = msda_bwd_sorted<VT, ROUNDS, true, GV16>;
         if (const int rc = configure(kernel, smem)) return rc;
         const int grid = sm_count() * (knob > 0 ? knob : resident_ctas(kernel, 256, smem, 1));
         kernel<<<grid, 256, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, *fa);
     } else {
-        auto kernel = msda_bwd_sorted<VT, ROUNDS, false>;
+        auto kernel = msda_bwd_sorted<VT, ROUNDS, false, GV16>;
         if (const int rc = configure(kernel, smem)) return rc;
         const int grid = sm_count() * (knob > 0 ? knob : resident_ctas(kernel, 256, smem, 1));
         kernel<<<grid, 256, smem, st>>>(go, value, shapes, start, loc, attn, gv, gl, ga, d, FusedArgs{});
     }
     return after_launch("msda_bwd_sorted");
+}
+
+// bf16 value with grad_value accumulated directly in bf16 (packed reds): the row-major kernel only
+int launch_bwd_sorted_gv16(const __nv_bfloat16 *go, const __nv_bfloat16 *value, const int64_t *shapes, const int64_t *start,
+                           const float *loc, const float *attn, uint16_t *gv16, float *gl, float *ga, const Dims &d,
+                           const FusedArgs *fa, cudaStream_t st) {
+    switch ((d.L * d.P + 7) / 8) {
+        case 1: return launch_bwd_sorted<__nv_bfloat16, 1, true>(go, value, shapes, start, loc, attn, gv16, gl, ga, d, fa, st);
+        case 2: return launch_bwd_sorted<__nv_bfloat16, 2, true>(go, value, shapes, start, loc, attn, gv16, gl, ga, d, fa, st);
+        case 3: return launch_bwd_sorted<__nv_bfloat16, 3, true>(go, value, shapes, start, loc, attn, gv16, gl, ga, d, fa, st);
+        default: return launch_bwd_sorted<__nv_bfloat16, 4, true>(go, value, shapes, start, loc, attn, gv16, gl, ga, d, fa, st);
+    }
 }
 
 // The decoder's shapes (a handful of queries per frame) give fewer passes than one wave has CTAs: those launches use
@@ -1164,9 +1177,25 @@ int msda_backward_bf16(const uint16_t *go, const uint16_t *value, const int64_t 
     if (const int rc = check_dims(N, S, M, D, L, Lq, P)) return rc;
     if (!tiled_ok(D, L, P) || g_force_generic.load())
         return fail(MSDA_ERR_UNSUPPORTED, "msda_backward_bf16: only channels == 32, num_levels <= 16, num_levels*num_point <= 32");
-    if (!gv32 && N > 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: null grad_value_f32");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nval = (int64_t)N * S * M * D;
+    if (!gv32 && gv16) {
+        // direct mode: grad_value accumulated in bf16 by packed reds (row-major kernel only), no fp32 buffer
+        if (L > kSortLevels) return fail(MSDA_ERR_UNSUPPORTED, "msda_backward_bf16: direct bf16 accumulation needs num_levels <= 4 (pass grad_value_f32)");
+        if (N > 0) {
+            const cudaError_t e = cudaMemsetAsync(gv16, 0, sizeof(uint16_t) * (size_t)nval, st);
+            if (e != cudaSuccess) return fail_cuda(e, "msda_backward_bf16: memset(grad_value)");
+        }
+        if ((int64_t)N * Lq == 0) return MSDA_OK;
+        if (!go || !value || !shapes || !start || !loc || !attn || !gl || !ga)
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: null pointer");
+        if (misaligned(value, 8) || misaligned(go, 8) || misaligned(gv16, 8) || misaligned(loc, 8) || misaligned(gl, 8))
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: misaligned pointer");
+        const Dims d = make_dims(N, S, M, D, L, Lq, P, 2);
+        return launch_bwd_sorted_gv16(reinterpret_cast<const __nv_bfloat16 *>(go), reinterpret_cast<const __nv_bfloat16 *>(value),
+                                      shapes, start, loc, attn, gv16, gl, ga, d, nullptr, st);
+    }
+    if (!gv32 && N > 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_bf16: null grad_value_f32 and grad_value_bf16");
     if (N > 0) {
         const cudaError_t e = cudaMemsetAsync(gv32, 0, sizeof(float) * (size_t)nval, st);
         if (e != cudaSuccess) return fail_cuda(e, "msda_backward_bf16: memset(grad_value)");
@@ -1266,6 +1295,26 @@ int msda_fused_backward_bf16(const uint16_t *go, const uint16_t *value, const in
                              int D, int L, int Lq, int P, float *gv32, uint16_t *gv16, float *g_off, float *g_logits,
                              float *g_loc, msda_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (!gv32 && gv16) {      // direct mode, see msda_backward_bf16
+        if (const int rc = check_dims(N, S, M, D, L, Lq, P)) return rc;
+        if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward: ref_dim must be 2 or 4");
+        if (!tiled_ok(D, L, P) || L > kSortLevels)
+            return fail(MSDA_ERR_UNSUPPORTED, "msda_fused_backward_bf16: direct bf16 accumulation needs channels == 32, num_levels <= 4, num_levels*num_point <= 32");
+        if (N > 0) {
+            const cudaError_t e = cudaMemsetAsync(gv16, 0, sizeof(uint16_t) * (size_t)N * S * M * D, st);
+            if (e != cudaSuccess) return fail_cuda(e, "msda_fused_backward_bf16: memset(grad_value)");
+        }
+        if ((int64_t)N * Lq == 0) return MSDA_OK;
+        if (!go || !value || !shapes || !start || !offsets || !logits || !ref || !g_off || !g_logits)
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward_bf16: null pointer");
+        if (misaligned(value, 8) || misaligned(go, 8) || misaligned(gv16, 8) || misaligned(offsets, 8) || misaligned(g_off, 8) ||
+            misaligned(ref, ref_dim == 2 ? 8 : 16) || (g_loc && misaligned(g_loc, 8)))
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_fused_backward_bf16: misaligned pointer");
+        const Dims d = make_dims(N, S, M, D, L, Lq, P, 2);
+        const FusedArgs fa{ref, ref_dim, nullptr, nullptr, g_loc};
+        return launch_bwd_sorted_gv16(reinterpret_cast<const __nv_bfloat16 *>(go), reinterpret_cast<const __nv_bfloat16 *>(value),
+                                      shapes, start, offsets, logits, gv16, g_off, g_logits, d, &fa, st);
+    }
     if (const int rc = fused_backward_any<__nv_bfloat16>("msda_fused_backward_bf16: null pointer",
                                                          reinterpret_cast<const __nv_bfloat16 *>(go),
                                                          reinterpret_cast<const __nv_bfloat16 *>(value), shapes, start, offsets,
