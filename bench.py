@@ -504,7 +504,7 @@ def run_ours(args):
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     bwd_kernel = "msda_bwd_sorted" if ocpg_b200.lib().msda_kernel_plan(vbytes, wl.n_heads, wl.head_dim, wl.L, wl.n_points) == 1 \
-        and wl.L <= 4 and wl.n_frames * wl.n_heads * ((wl.n_queries + 31) // 32) > 2 * torch.cuda.get_device_properties(dev).multi_processor_count \
+        and wl.L <= 4 and wl.n_queries == wl.S and wl.n_frames * wl.n_heads * ((wl.n_queries + 31) // 32) > 2 * torch.cuda.get_device_properties(dev).multi_processor_count \
         else "msda_bwd_tiled"
     if rank == 0:
         # The two on-chip resources that actually bound the kernels, from counters of the committed ncu

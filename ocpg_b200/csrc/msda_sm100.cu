@@ -57,7 +57,7 @@ std::atomic<int> g_skip_scatter{0};      // see Dims::debug_skip_scatter
 std::atomic<int> g_unit{0};               // 0 = automatic; frames interleaved by the task walk
 std::atomic<int> g_force_generic{0};
 std::atomic<int> g_force_linear{0};     // experiments: never use the tiled query walk
-std::atomic<int> g_bwd_algo{0};         // 0 = automatic (row-major "sorted" kernel unless the launch is under-filled), 1 = query-major msda_bwd_tiled
+std::atomic<int> g_bwd_algo{0};         // 0 = automatic (row-major msda_bwd_sorted for encoder shapes, Lq == S, unless under-filled), 1 = query-major msda_bwd_tiled, 2 = row-major for any filled launch
 std::atomic<int> g_bwd_deep{0};         // 0 = automatic (under-filled launches), 1 = always, -1 = never: msda_bwd_tiled<.., DEEP>
 
 int fail(int code, const char *msg) {
@@ -1009,7 +1009,11 @@ int launch_bwd_one(const VT *go, const VT *value, const int64_t *shapes, const i
             return launch_bwd_kernel<VT, ROUNDS, 8, true>(sm_count(), go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
     }
     if constexpr (WARPS == 8) {
-        if (g_bwd_algo.load() != 1 && d.L <= kSortLevels) return launch_bwd_sorted<VT, ROUNDS>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
+        // Row-major kernel for the encoder's self-attention (Lq == S: neighbouring queries sample neighbouring rows, which is
+        // what its per-tile sort merges); object queries (Lq != S) have no such locality: query-major kernel.  bwd_algo = 2
+        // forces the row-major kernel for any shape.
+        const int algo = g_bwd_algo.load();
+        if (algo != 1 && d.L <= kSortLevels && (d.tiled || algo == 2)) return launch_bwd_sorted<VT, ROUNDS>(go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
     }
     return launch_bwd_kernel<VT, ROUNDS, WARPS, false>(grid, go, value, shapes, start, loc, attn, gv, gl, ga, d, fa, st);
 }

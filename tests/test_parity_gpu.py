@@ -375,12 +375,41 @@ def test_more_than_2_31_value_elements(dev, dtype):
     assert torch.isfinite(gv[::97].float()).all() and gv[N - 1].float().abs().max().item() > 0
 
 
+def test_maximum_collisions_in_one_cell(dev):
+    """Every point of every query at the SAME location (2048 items of a tile in one histogram cell: the longest possible
+    runs), and the same with all points just outside the level (nothing valid): the sort's edge cases."""
+    from ocpg_b200.workloads import encoder_workload, make_inputs
+    wl = encoder_workload("t", 2, 128, 256)          # levels 16x32, 8x16, 4x8, 2x4
+    x = make_inputs(wl, "init", seed=23)
+    x["loc"][..., 0] = 0.4321
+    x["loc"][..., 1] = 0.6789
+    check(ours(x, dev), oracle64(x), x)
+    x["loc"][..., 0] = 1.2
+    out, gv, gl, ga = ours(x, dev)
+    assert not out.any() and not gv.any() and not gl.any() and not ga.any()
+
+
 def test_measurement_switches_are_not_in_the_product_build(dev):
     """bwd_mode / debug_skip_scatter return wrong gradients by design: they exist only in -DMSDA_EXPERIMENTS builds."""
     import ocpg_b200
     for key in ("bwd_mode", "debug_skip_scatter"):
         with pytest.raises(RuntimeError, match="MSDA_EXPERIMENTS"):
             ocpg_b200.set_option(key, 1)
+
+
+def test_row_major_backward_on_object_query_shapes(dev):
+    """Lq != S (linear query walk, no spatial coherence between the 32 queries of a tile: nearly every item is loose):
+    bwd_algo = 2 forces msda_bwd_sorted there; the default for such shapes is the query-major kernel."""
+    import ocpg_b200
+    from ocpg_b200.workloads import Workload, A2D_ENCODER, make_inputs
+    wl = Workload("q300", 4, A2D_ENCODER.levels, 300)
+    ocpg_b200.set_option("bwd_algo", 2)
+    try:
+        for regime in ("init", "uniform"):
+            x = make_inputs(wl, regime, seed=29)
+            check(ours(x, dev), oracle64(x), x)
+    finally:
+        ocpg_b200.set_option("bwd_algo", 0)
 
 
 @pytest.mark.parametrize("algo", [0, 1])
