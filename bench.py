@@ -515,11 +515,15 @@ def run_ours(args):
             sms, mhz = torch.cuda.get_device_properties(dev).multi_processor_count, (clk or {}).get("sm_mhz") or 1965.0
             red_gbs = traffic["bwd_red_bytes"] / (bwd_ms * 1e-3) / 1e9
             line_rate = traffic["fwd_l1_lines"] / (fwd_ms * 1e-3) / (sms * mhz * 1e6)
-            on_chip = {"bwd": {"bound": "L2 fp32 atomic units", "achieved": red_gbs, "peak": oc.get("l2_fp32_atomic_peak_gbs"),
-                               "unit": "GB/s of red sectors", "frac": red_gbs / oc["l2_fp32_atomic_peak_gbs"] if oc.get("l2_fp32_atomic_peak_gbs") else None},
-                       "fwd": {"bound": "L1 line rate (gather only, without the per-point broadcasts)", "achieved": line_rate,
-                               "peak": oc.get("l1_lines_per_clk_per_sm"), "unit": "128-byte lines per clock per SM", "frac": line_rate},
-                       "source": oc.get("source")}
+            on_chip = {"bwd": {"bound": "SM load/store data path (shared memory + L1: 128 B per clock per SM) -- the row-major kernel's limit; "
+                                        "its reds use the L2 fp32 atomic units at `l2_atomic_frac`",
+                               "lsu_data_pipe_busy_pct": traffic.get("bwd_lsu_data_pipe_pct"), "red_sector_gbs": red_gbs,
+                               "l2_atomic_peak_gbs": oc.get("l2_fp32_atomic_peak_gbs"),
+                               "l2_atomic_frac": red_gbs / oc["l2_fp32_atomic_peak_gbs"] if oc.get("l2_fp32_atomic_peak_gbs") else None},
+                       "fwd": {"bound": "SM load/store data path: L1 line rate of the gather (without the per-point broadcasts)", "achieved": line_rate,
+                               "peak": oc.get("l1_lines_per_clk_per_sm"), "unit": "128-byte lines per clock per SM", "frac": line_rate,
+                               "lsu_data_pipe_busy_pct": traffic.get("fwd_lsu_data_pipe_pct")},
+                       "source": (oc.get("source") or "") + "; lsu_data_pipe_busy_pct = l1tex__data_pipe_lsu_wavefronts of the committed ncu capture"}
         line = {
             "metric": METRIC, "value": value_qps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

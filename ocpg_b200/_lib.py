@@ -63,17 +63,38 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def _code_only(text: str) -> str:
+    """C/C++ source with comments and all whitespace removed (string literals kept verbatim)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == '"' or c == "'":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1]); i = j + 1
+        elif text.startswith("//", i):
+            j = text.find("\n", i); i = n if j < 0 else j
+        elif text.startswith("/*", i):
+            j = text.find("*/", i + 2); i = n if j < 0 else j + 2
+        elif c.isspace():
+            i += 1
+        else:
+            out.append(c); i += 1
+    return "".join(out)
+
+
 def source_fingerprint() -> str:
-    """First 16 hex digits of the SHA-256 of the kernel sources (csrc/*, include/msda_sm100.h): ties profiles (ncu
-    captures, profiles/traffic.json) to the kernels they were taken from."""
+    """First 16 hex digits of the SHA-256 of the kernel sources' CODE (csrc/*, include/msda_sm100.h; comments and
+    whitespace do not count): ties profiles (ncu captures, profiles/traffic.json) to the kernels they were taken from."""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(_PKG, "csrc")
     for f in sorted(os.listdir(csrc)) + [os.path.join(INCLUDE, "msda_sm100.h")]:
         path = f if os.path.isabs(f) else os.path.join(csrc, f)
         if path.endswith((".cu", ".cuh", ".h")):
-            with open(path, "rb") as fh:
-                h.update(os.path.basename(path).encode() + b"\0" + fh.read())
+            with open(path, "r", encoding="utf-8") as fh:
+                h.update(os.path.basename(path).encode() + b"\0" + _code_only(fh.read()).encode())
     return h.hexdigest()[:16]
 
 

@@ -10,8 +10,10 @@
 // Neither is served by HBM.  Measured on this machine (tools/ubench_gather.cu, profiles/r1_ubench_*.jsonl):
 //   - a four-row LDG.128 costs an SM 4.1 cycles when all rows hit L1 and 8.1 cycles when one misses; rows
 //     straight from L2 stream at ~2 cycles each (64 B/clk/SM);
-//   - fp32 reds are bounded CHIP-wide by the L2 atomic units: 6.4 TB/s however they are issued (v4, v2, scalar;
-//     37 or 148 SMs), and far less when many CTAs hit the same few rows.
+//   - fp32 reds are bounded CHIP-wide by the L2 atomic units: 6.4 TB/s however they are issued (v4, v2, scalar, TMA bulk
+//     reduce; 37 or 148 SMs), and far less when many CTAs hit the same few rows;
+//   - LDS, LDG hits AND warp shuffles share one 128-byte-per-clock data path per SM (tools/ubench_pipes.cu): it is what
+//     both kernels end up bound by.
 // So:
 //   1. few, wide memory instructions: 8 lanes x 128-bit cover one 32-channel row, the four 8-lane groups of a
 //      warp work on four x-adjacent queries, so one LDG.128 / RED.128 moves four rows;

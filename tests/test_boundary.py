@@ -288,3 +288,17 @@ def test_strict_mode_raises_instead_of_falling_back_to_torch():
                 call()
     finally:
         ocpg_b200.set_strict(False)
+
+
+def test_source_fingerprint_ignores_comments_and_tags_the_committed_capture():
+    """profiles/traffic.json entries are only used by bench.py when they were captured from the kernel code built now."""
+    import json
+    import ocpg_b200
+    from ocpg_b200 import _lib
+    assert _lib._code_only('int a = 1; // note\n/* block */ const char *s = "// kept";\n') == 'inta=1;constchar*s="// kept";'
+    fp = ocpg_b200.source_fingerprint()
+    assert len(fp) == 16 and fp == ocpg_b200.source_fingerprint()
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        table = json.load(f)
+    entries = [v for k, v in table.items() if not k.startswith("_")]
+    assert entries and all("kernel_sources" in e for e in entries)
