@@ -32,6 +32,17 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["auto", "filled"])
+def launch_kind(request):
+    """Small test shapes give fewer passes than 2 x SMs and would only ever run the under-filled (DEEP, query-major)
+    backward; "filled" switches that heuristic off (bwd_deep = -1), so the same shapes run the production kernels of the
+    BASELINE shapes (msda_bwd_sorted for Lq == S)."""
+    import ocpg_b200
+    ocpg_b200.set_option("bwd_deep", -1 if request.param == "filled" else 0)
+    yield request.param
+    ocpg_b200.set_option("bwd_deep", 0)
+
+
 def ours(x, dev, dtype=torch.float32, value_dtype=None):
     """Run forward + backward through the C-ABI shim; returns numpy (out, gv, gl, ga)."""
     import ocpg_b200.MultiScaleDeformableAttention as MSDA
@@ -79,7 +90,7 @@ def test_golden_fp64(golden, dev):
     check(got, want, golden, fwd_tol=1e-12, bwd_tol=1e-11, eps=1e-9)
 
 
-def test_golden_fp32(golden, dev):
+def test_golden_fp32(golden, dev, launch_kind):
     import ocpg_b200
     got = ours(golden, dev, torch.float32)
     want = tuple(golden[k] for k in ("out", "grad_value", "grad_loc", "grad_attn"))
@@ -194,7 +205,7 @@ def test_gapped_level_start_index_falls_back_to_linear_walk(dev):
 
 
 @pytest.mark.parametrize("L,P", [(1, 1), (2, 3), (3, 8), (4, 8), (5, 4), (16, 2), (4, 9)])
-def test_level_point_combinations(dev, L, P):
+def test_level_point_combinations(dev, L, P, launch_kind):
     """D = 32 with other L / P: 1..4 staging rounds of the tiled kernel, and (4, 9) -> generic."""
     g = torch.Generator().manual_seed(L * 100 + P)
     hw = [(max(1, 12 >> l), max(1, 10 >> l)) for l in range(L)]
@@ -235,7 +246,7 @@ def test_nonfinite_locations_are_out_of_range(dev):
 # ------------------------------------------------------------------------------------------------
 # bf16 value
 # ------------------------------------------------------------------------------------------------
-def test_bf16_value_vs_oracle(dev):
+def test_bf16_value_vs_oracle(dev, launch_kind):
     """Tolerance: against the fp64 oracle fed the bf16-ROUNDED value and grad_output (isolates kernel
     arithmetic from input quantisation): fp32-emitted grads 1e-4; bf16-emitted out / grad_value
     2^-8 = 3.9e-3 (one bf16 rounding of the result)."""
@@ -286,7 +297,7 @@ def test_full_shapes_vs_oracle_fp32_and_bf16(dev, config, regime):
 
 @pytest.mark.parametrize("ref_dim", [2, 4])
 @pytest.mark.parametrize("emit", [True, False])
-def test_fused_bf16_vs_oracle(dev, ref_dim, emit):
+def test_fused_bf16_vs_oracle(dev, ref_dim, emit, launch_kind):
     """msda_fused_{forward,backward}_bf16 (bf16 value / output / grad_output, fp32 offsets, logits, reference points)
     against the fp64 oracle fed the locations / probabilities the fused kernel itself must produce (torch formulation of
     ms_deform_attn.py:101-110 in fp64 on the same fp32 inputs), with the softmax / offset chain rule applied in fp64."""
@@ -526,7 +537,7 @@ class _OracleModule(torch.nn.Module):
 
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("ref_dim,use_mask", [(2, False), (2, True), (4, False)])
-def test_module_end_to_end(dev, ref_dim, use_mask, fused):
+def test_module_end_to_end(dev, ref_dim, use_mask, fused, launch_kind):
     from ocpg_b200 import MSDeformAttn
     from oracle.compare import rel_err
     torch.manual_seed(0)
@@ -565,7 +576,7 @@ def test_module_end_to_end(dev, ref_dim, use_mask, fused):
 
 @pytest.mark.parametrize("ref_dim", [2, 4])
 @pytest.mark.parametrize("regime", ["init", "uniform"])
-def test_fused_operator_matches_unfused(dev, ref_dim, regime):
+def test_fused_operator_matches_unfused(dev, ref_dim, regime, launch_kind):
     """MSDeformAttnFusedFunction == softmax + location arithmetic in torch followed by MSDeformAttnFunction:
     locations bit-identical (same operation order), everything else within a few fp32 ulps."""
     from ocpg_b200 import MSDeformAttnFunction, MSDeformAttnFusedFunction
@@ -670,7 +681,7 @@ def test_fused_rejects_unsupported_layouts(dev):
 
 
 @pytest.mark.parametrize("fused", [True, False])
-def test_encoder_layers_vs_fp64_oracle(dev, fused):
+def test_encoder_layers_vs_fp64_oracle(dev, fused, launch_kind):
     """The caller of the hot path (deformable_transformer.py:220-290): a 2-layer encoder forward + backward on the
     GPU vs the same weights in fp64 with the op replaced by the grid_sample port, incl. valid_ratios < 1, positional
     embeddings and a padding mask."""
