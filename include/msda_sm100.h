@@ -87,7 +87,9 @@ int msda_backward_f64(const double *grad_output, const double *value, const int6
                       msda_stream_t stream);
 
 /* ---- bf16 value (new; value / output / grad_output are bf16 bit patterns, loc and attn stay fp32,
- *      accumulation is fp32).  grad_value is accumulated in the fp32 buffer grad_value_f32
+ *      accumulation is fp32).  grad_value_f32 == NULL with grad_value_bf16 != NULL selects direct accumulation in bf16
+ *      (packed bf16 reds, row-major kernel, num_levels <= 4: ~4-6 % of max error); otherwise
+ *      grad_value is accumulated in the fp32 buffer grad_value_f32
  *      (same shape as value, zero-filled by the call); if grad_value_bf16 is non-NULL the rounded
  *      result is also written there. ---- */
 int msda_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -242,17 +244,19 @@ int msda_kernel_plan(int elem_bytes, int num_heads, int channels, int num_levels
  * used by bench.py to report `gpu_launches`. */
 uint64_t msda_launch_count(void);
 
-/* Tuning knobs for experiments (not needed for normal use).  Known keys:
- *   "fwd_warps", "bwd_warps"             8 or 16 warps per CTA (0 = default)
+/* Tuning knobs (not needed for normal use; every setting returns correct results).  Known keys:
+ *   "fwd_warps", "bwd_warps"             8 or 16 warps per CTA of the query-major kernels (0 = default)
  *   "fwd_ctas_per_sm", "bwd_ctas_per_sm" resident CTAs per SM the persistent grid is sized for (0 = default)
  *   "frame_chunk"                        frames whose passes are interleaved by the task walk (0 = automatic)
  *   "force_generic"                      use the any-shape kernels even when the tiled ones apply
  *   "force_linear_walk"                  walk queries linearly instead of as spatial tiles
- *   "bwd_mode"                           1 = backward without the grad_value scatter, 2 = the scatter alone
- *   "debug_skip_scatter"                 same as bwd_mode 1
- *   "bwd_deep"                           backward variant that issues a round's 32 row loads before their first use:
- *                                        0 = automatic (launches with fewer passes than SMs), 1 = always, -1 = never
- * (the last two make results wrong on purpose: they exist to measure what bounds the backward).
+ *   "bwd_algo"                           0 = automatic: the row-major backward msda_bwd_sorted for encoder shapes
+ *                                        (num_query == spatial_size, num_levels <= 4), the query-major msda_bwd_tiled
+ *                                        otherwise; 1 = always query-major; 2 = row-major for any filled launch
+ *   "bwd_deep"                           under-filled-launch backward variant (a round's 32 row loads issued before their
+ *                                        first use): 0 = automatic (fewer passes than 2 x SMs), 1 = always, -1 = never
+ * The measurement-only switches "bwd_mode" / "debug_skip_scatter" (they omit the grad_value scatter) exist only in
+ * -DMSDA_EXPERIMENTS builds of the library; the product build answers MSDA_ERR_UNSUPPORTED.
  * Returns 0, or MSDA_ERR_INVALID_ARGUMENT for an unknown key. */
 int msda_set_option(const char *key, int value);
 
