@@ -28,6 +28,17 @@
 //           back to the owners through shared memory;
 //   finish  the owner of a (query, point) combines its four p's exactly like msda_bwd_tiled (cuh:123-158 regrouped).
 //
+// Shared-memory ordering is by the CTA barriers S1..S6 alone (no warp-level assumptions).  Per array, writer -> readers:
+//   go     stage (before S1)            -> walk (S5..S6); next writer: next tile's stage, after S6
+//   stat   stage atomics (before S1)    -> histogram (S1..S2); reset in the scan (after S2), next atomics after S6
+//   hist   histogram atomics (S1..S2)   -> scan (S2..S4, rewrites .y) -> place (S4..S5); cleared in the walk (after S5),
+//                                          next atomics after the next S1
+//   win_*  histogram phase (S1..S2)     -> scan (S3..S4); next writer after the next S1
+//   n_overflow  histogram (S1..S2)      -> place (S4..S5, every thread reads it); reset in the walk (after S5)
+//   n_runs, n_win_loose, warp_tot       scan (S2..S4) -> scan / place (..S5); next writer after the next S2
+//   items, rows  place (S4..S5)         -> walk (S5..S6); next writer after the next S4
+//   p      walk (S5..S6)                -> finish (after S6); next writer after the next S5
+//
 // Row loads and reds drop 2.4x on the A2D / YTVOS encoder shapes in the init regime (642 per tile instead of 1532); what
 // is left per item is one 128-byte shared-memory read and ~10 instructions.
 #pragma once
