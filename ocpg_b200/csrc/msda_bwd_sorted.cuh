@@ -297,9 +297,10 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
             __syncthreads();                                                                    // S3
             uint32_t excl = incl - tsum;
             for (int w = 0; w < warp; ++w) excl += sm.warp_tot[w];
-            if (tsum) {
+            if (tsum) {      // 16-byte stores: lanes 48 bytes apart cover all banks (4-byte stores of .y alone conflict 4-way)
 #pragma unroll
-                for (int k = 0; k < 6; ++k) sm.hist[c0 + k].y = excl + pre[k];
+                for (int k = 0; k < 6; k += 2)
+                    *reinterpret_cast<uint4 *>(&sm.hist[c0 + k]) = make_uint4(cnt[k], excl + pre[k], cnt[k + 1], excl + pre[k + 1]);
             }
             if (tid == 255) {
                 sm.n_runs = (excl + tsum) & 0xffffu;
