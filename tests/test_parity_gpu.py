@@ -400,6 +400,39 @@ def test_maximum_collisions_in_one_cell(dev):
     assert not out.any() and not gv.any() and not gl.any() and not ga.any()
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_encoder_geometries(dev, seed):
+    """Seeded random encoder-like problems (Lq == S): 1-4 levels of arbitrary small shapes (1 x 1 levels, single rows and
+    columns included), 1-8 points, 1-8 heads, locations from tightly clustered to far out of range -- forward and both
+    backward kernels (the launch heuristic switched off, so the row-major kernel runs whatever the size) against the oracle."""
+    import ocpg_b200
+    rng = np.random.default_rng(1000 + seed)
+    L = int(rng.integers(1, 5))
+    P = int(rng.choice([1, 2, 3, 4, 8]))
+    M = int(rng.choice([1, 2, 8]))
+    N = int(rng.integers(1, 4))
+    hw = [(int(rng.integers(1, 41)), int(rng.integers(1, 41))) for _ in range(L)]
+    g = torch.Generator().manual_seed(2000 + seed)
+    shapes = torch.tensor(hw)
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    spread = float(rng.choice([0.02, 0.2, 1.0]))
+    centre = torch.rand(N, S, 1, 1, 1, 2, generator=g)
+    loc = centre + (torch.rand(N, S, M, L, P, 2, generator=g) - 0.5) * spread * 1.4
+    x = dict(value=torch.randn(N, S, M, 32, generator=g), shapes=shapes, start=start, loc=loc.contiguous(),
+             attn=torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P),
+             grad_out=torch.randn(N, S, M * 32, generator=g))
+    want = oracle64(x)
+    ocpg_b200.set_option("bwd_deep", -1)
+    try:
+        for algo in (0, 1):
+            ocpg_b200.set_option("bwd_algo", algo)
+            check(ours(x, dev), want, x)
+    finally:
+        ocpg_b200.set_option("bwd_algo", 0)
+        ocpg_b200.set_option("bwd_deep", 0)
+
+
 def test_measurement_switches_are_not_in_the_product_build(dev):
     """bwd_mode / debug_skip_scatter return wrong gradients by design: they exist only in -DMSDA_EXPERIMENTS builds."""
     import ocpg_b200
