@@ -83,7 +83,7 @@ def main():
             measure("default")
             if wl is not A2D_DECODER:
                 measure("linear_walk", force_linear_walk=1)
-                measure("bwd_no_scatter(debug)", debug_skip_scatter=1)
+                measure("bwd_query_major", bwd_algo=1)
                 measure("fwd1cta_bwd1cta", fwd_ctas_per_sm=1, bwd_ctas_per_sm=1)
                 if not args.quick:
                     measure("fwd3", fwd_ctas_per_sm=3)
