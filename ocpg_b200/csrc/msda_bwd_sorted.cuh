@@ -31,7 +31,7 @@
 // Shared-memory ordering is by the CTA barriers S1..S6 alone (no warp-level assumptions).  Per array, writer -> readers:
 //   go     stage (before S1)            -> walk (S5..S6); next writer: next tile's stage, after S6
 //   stat   stage atomics (before S1)    -> histogram (S1..S2); reset in the scan (after S2), next atomics after S6
-//   hist   histogram atomics (S1..S2)   -> scan (S2..S4, rewrites .y) -> place (S4..S5); cleared in the walk (after S5),
+//   hist   histogram atomics (S1..S2)   -> scan (S2..S4; it writes cell_pos) -> place (S4..S5); cleared in the walk (after S5),
 //                                          next atomics after the next S1
 //   win_*  histogram phase (S1..S2)     -> scan (S3..S4); next writer after the next S1
 //   n_overflow  histogram (S1..S2)      -> place (S4..S5, every thread reads it); reset in the walk (after S5)
@@ -62,7 +62,8 @@ template <int ROUNDS> struct SortSmem {
     int stat[kSortLevels][4];                                    // sum x0, sum y0, points in range (this tile)
     uint32_t warp_tot[8];
     uint32_t n_runs, n_win_loose, n_overflow, pad_;
-    alignas(16) uint2 hist[kSortCells];                          // per window cell: {items, runs before | loose items before << 16}
+    alignas(16) uint32_t hist[kSortCells];                       // items per window cell (a plain u32 array: the atomics use all 32 banks)
+    alignas(16) uint32_t cell_pos[kSortCells];                   // per window cell: runs before | loose items before << 16
     uint32_t rows[kItems];                                       // row (unit offset) of run r at [r], of loose item i at [kItems-1-i]
     alignas(16) uint2 items[kSlots + 4];                                     // {grad_out row offset | p slot << 16, a * w_corner}
     float4 go[kQueries][8];                                      // grad_out rows of the tile's queries, fp32
@@ -160,7 +161,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
     load_level_table<WARPS>(lt, shapes, start, d.L, d.Lq);
     if (tid == 0) sm.n_overflow = 0;
     if (tid < 4) sm.items[SM::kSlots + tid] = make_uint2(SM::kDummySlot << 16, 0u);       // the null run
-    for (int i = tid; i < kSortCells; i += 256) sm.hist[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < kSortCells; i += 256) sm.hist[i] = 0u;
     if (tid < kSortLevels * 4) (&sm.stat[0][0])[tid] = 0;
     __syncthreads();
     const bool tiled = d.tiled && lt.dense;
@@ -262,7 +263,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                 if ((mask[r] >> (4 + c)) & 1u) ++out_rank;
                 if ((mask[r] >> c) & 1u) {
                     SORT_CHECK((unsigned)(cell00[r] + (c & 1) + (c >> 1) * kWinX) < (unsigned)kSortCells);
-                    rk[c] = atomicAdd(&sm.hist[cell00[r] + (c & 1) + (c >> 1) * kWinX].x, 1u);
+                    rk[c] = atomicAdd(&sm.hist[cell00[r] + (c & 1) + (c >> 1) * kWinX], 1u);
                 }
             }
             rank[r][0] = rk[0] | (rk[1] << 16);
@@ -276,8 +277,8 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
             uint32_t cnt[6], tsum = 0;
 #pragma unroll
             for (int k = 0; k < 6; k += 2) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(&sm.hist[c0 + k]);
-                cnt[k] = v.x; cnt[k + 1] = v.z;
+                const uint2 v = *reinterpret_cast<const uint2 *>(&sm.hist[c0 + k]);
+                cnt[k] = v.x; cnt[k + 1] = v.y;
             }
             uint32_t pre[6];
 #pragma unroll
@@ -297,10 +298,10 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
             __syncthreads();                                                                    // S3
             uint32_t excl = incl - tsum;
             for (int w = 0; w < warp; ++w) excl += sm.warp_tot[w];
-            if (tsum) {      // 16-byte stores: lanes 48 bytes apart cover all banks (4-byte stores of .y alone conflict 4-way)
+            if (tsum) {
 #pragma unroll
                 for (int k = 0; k < 6; k += 2)
-                    *reinterpret_cast<uint4 *>(&sm.hist[c0 + k]) = make_uint4(cnt[k], excl + pre[k], cnt[k + 1], excl + pre[k + 1]);
+                    *reinterpret_cast<uint2 *>(&sm.cell_pos[c0 + k]) = make_uint2(excl + pre[k], excl + pre[k + 1]);
             }
             if (tid == 255) {
                 sm.n_runs = (excl + tsum) & 0xffffu;
@@ -327,7 +328,10 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                 const uint32_t rk = (rank[r][c >> 1] >> (16 * (c & 1))) & 0xffffu;
                 const uint32_t unit = unit00 + (uint32_t)((c & 1) * pixel_units + (c >> 1) * row_step);
                 uint2 h = make_uint2(0u, 0u);      // {items of the cell, runs before | loose before << 16}
-                if (inw) h = sm.hist[cell00[r] + (c & 1) + (c >> 1) * kWinX];
+                if (inw) {
+                    const int cell = cell00[r] + (c & 1) + (c >> 1) * kWinX;
+                    h = make_uint2(sm.hist[cell], sm.cell_pos[cell]);
+                }
                 const uint32_t rem = h.x & 3u;
                 const uint32_t run_items = rem == 3u ? h.x : h.x - rem;      // the first run_items ranks of the cell go to runs
                 const bool in_run = rk < run_items;                           // false outside the window (run_items = 0)
@@ -350,7 +354,7 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
         {
             if (tid == 0) sm.n_overflow = 0;          // every thread read it before S5; its next writer comes after S1
             // the histogram is dead: clear it for the next tile (its next writer comes after S6 / S1)
-            for (int i = tid; i < kSortCells / 2; i += 256) reinterpret_cast<uint4 *>(sm.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < kSortCells / 4; i += 256) reinterpret_cast<uint4 *>(sm.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
             const char *go_lane = reinterpret_cast<const char *>(&sm.go[0][cl]);
             float *p_flat = reinterpret_cast<float *>(sm.p);
             auto go_row = [&](uint32_t tag) -> Row {
