@@ -399,33 +399,36 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                     has = has_next; unit = unit_next; ip = ip_next; v = v_next;
                 }
             }
-            // loose items: one per lane group and step, each with its own row; two steps in flight
-            for (int base = warp * 4; base < n_loose; base += 64) {
-                uint2 it[2];
-                uint32_t unit[2];
-                bool has[2];
-                Row v[2];
+            // loose items: four per lane group and step, each with its own row load and its own red; their dot products share
+            // one butterfly -- the same summation tree as the runs' (lane pairs 4 apart first): whether an item lands in a run or
+            // here depends on the order of the histogram atomics, and d/d location, d/d attention stay bitwise reproducible
+            for (int base = warp * 4; base < n_loose; base += 128) {
+                uint2 it[4];
+                uint32_t unit[4];
+                Row v[4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const int li = base + 32 * u + grp;
-                    has[u] = li < n_loose;
-                    it[u] = sm.items[has[u] ? SM::kSlots - 1 - li : SM::kSlots];
-                    unit[u] = has[u] ? sm.rows[SM::kItems - 1 - li] : 0u;
-                    v[u] = IO::load_stream(row_at(vb, unit[u]));
+                    const bool has = li < n_loose;
+                    it[u] = sm.items[has ? SM::kSlots - 1 - li : SM::kSlots];      // none: the null item (weight 0, dummy p slot)
+                    unit[u] = has ? sm.rows[SM::kItems - 1 - li] : 0xffffffffu;
+                    v[u] = IO::load_stream(row_at(vb, has ? unit[u] : 0u));
                 }
+                float ds[4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const Row g = go_row(it[u].x);
                     const float aw = __uint_as_float(it[u].y);
-                    float dsum = dot_row(g, v[u]);
-                    red_run<GV16>(gb, unit[u], Row{__fmul2_rn(splat(aw), g.lo), __fmul2_rn(splat(aw), g.hi)}, has[u]);
-                    // same summation tree as the runs' butterfly (lane pairs 4 apart first): whether an item lands in a run or
-                    // here depends on the order of the histogram atomics, and d/d location, d/d attention stay bitwise reproducible
-                    dsum += __shfl_xor_sync(kFull, dsum, 4);
-                    dsum += __shfl_xor_sync(kFull, dsum, 2);
-                    dsum += __shfl_xor_sync(kFull, dsum, 1);
-                    if (cl == 0) p_flat[it[u].x >> 16] = dsum;
+                    ds[u] = dot_row(g, v[u]);
+                    red_run<GV16>(gb, unit[u], Row{__fmul2_rn(splat(aw), g.lo), __fmul2_rn(splat(aw), g.hi)}, unit[u] != 0xffffffffu);
                 }
+                const bool up4 = (cl & 4) != 0, up2 = (cl & 2) != 0;
+                const float e0 = (up4 ? ds[2] : ds[0]) + __shfl_xor_sync(kFull, up4 ? ds[0] : ds[2], 4);
+                const float e1 = (up4 ? ds[3] : ds[1]) + __shfl_xor_sync(kFull, up4 ? ds[1] : ds[3], 4);
+                float tot = (up2 ? e1 : e0) + __shfl_xor_sync(kFull, up2 ? e0 : e1, 2);
+                tot += __shfl_xor_sync(kFull, tot, 1);
+                const uint32_t my_tag = up4 ? (up2 ? it[3].x : it[2].x) : (up2 ? it[1].x : it[0].x);
+                if (!(cl & 1)) p_flat[my_tag >> 16] = tot;
             }
         }
         __syncthreads();                                                                        // S6: dot products complete
