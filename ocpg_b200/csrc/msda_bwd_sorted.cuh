@@ -63,7 +63,10 @@ template <int ROUNDS> struct SortSmem {
     uint32_t warp_tot[8];
     uint32_t n_runs, n_win_loose, n_overflow, pad_;
     alignas(16) uint32_t hist[kSortCells];                       // items per window cell (a plain u32 array: the atomics use all 32 banks)
-    alignas(16) uint32_t cell_pos[kSortCells];                   // per window cell: runs before | loose items before << 16
+    // per window cell, written by the scan: runs before | loose items before << 16 -- or, when the tile has at most 2048 items
+    // (kPacked), everything the place phase needs in one word: runs before | loose before << 10 | (items - 1) << 21
+    static constexpr bool kPacked = kItems <= 2048;
+    alignas(16) uint32_t cell_pos[kSortCells];
     uint32_t rows[kItems];                                       // row (unit offset) of run r at [r], of loose item i at [kItems-1-i]
     alignas(16) uint2 items[kSlots + 4];                                     // {grad_out row offset | p slot << 16, a * w_corner}
     float4 go[kQueries][8];                                      // grad_out rows of the tile's queries, fp32
@@ -300,8 +303,14 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
             for (int w = 0; w < warp; ++w) excl += sm.warp_tot[w];
             if (tsum) {
 #pragma unroll
-                for (int k = 0; k < 6; k += 2)
-                    *reinterpret_cast<uint2 *>(&sm.cell_pos[c0 + k]) = make_uint2(excl + pre[k], excl + pre[k + 1]);
+                for (int k = 0; k < 6; k += 2) {
+                    uint32_t a0 = excl + pre[k], a1 = excl + pre[k + 1];
+                    if constexpr (SM::kPacked) {
+                        a0 = (a0 & 0xffffu) | ((a0 >> 16) << 10) | ((cnt[k] - 1u) << 21);
+                        a1 = (a1 & 0xffffu) | ((a1 >> 16) << 10) | ((cnt[k + 1] - 1u) << 21);
+                    }
+                    *reinterpret_cast<uint2 *>(&sm.cell_pos[c0 + k]) = make_uint2(a0, a1);
+                }
             }
             if (tid == 255) {
                 sm.n_runs = (excl + tsum) & 0xffffu;
@@ -330,7 +339,12 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
                 uint2 h = make_uint2(0u, 0u);      // {items of the cell, runs before | loose before << 16}
                 if (inw) {
                     const int cell = cell00[r] + (c & 1) + (c >> 1) * kWinX;
-                    h = make_uint2(sm.hist[cell], sm.cell_pos[cell]);
+                    if constexpr (SM::kPacked) {
+                        const uint32_t w = sm.cell_pos[cell];
+                        h = make_uint2((w >> 21) + 1u, (w & 0x3ffu) | (((w >> 10) & 0x7ffu) << 16));
+                    } else {
+                        h = make_uint2(sm.hist[cell], sm.cell_pos[cell]);
+                    }
                 }
                 const uint32_t rem = h.x & 3u;
                 const uint32_t run_items = rem == 3u ? h.x : h.x - rem;      // the first run_items ranks of the cell go to runs
