@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """bwd_pdl = 1: zero-fill of grad_value by msda_zero_fill with the row-major backward as its programmatic dependent.
-Checks results against bwd_pdl = 0 (eager and inside a CUDA graph) and times both."""
+Checks results against bwd_pdl = 0 (eager and inside a CUDA graph) and times both.
+ARCHIVED: the `bwd_pdl` option was measured (slower, tools/experiments/README.md) and is not in the library; this script
+documents how it was checked."""
 import json, os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
