@@ -33,7 +33,6 @@
 //   stat   stage atomics (before S1)    -> histogram (S1..S2); reset in the scan (after S2), next atomics after S6
 //   hist   histogram atomics (S1..S2)   -> scan (S2..S4; it writes cell_pos) -> place (S4..S5); cleared in the walk (after S5),
 //                                          next atomics after the next S1
-//   win_*  histogram phase (S1..S2)     -> scan (S3..S4); next writer after the next S1
 //   n_overflow  histogram (S1..S2)      -> place (S4..S5, every thread reads it); reset in the walk (after S5)
 //   n_runs, n_win_loose, warp_tot       scan (S2..S4) -> scan / place (..S5); next writer after the next S2
 //   items, rows  place (S4..S5)         -> walk (S5..S6); next writer after the next S4
@@ -58,7 +57,6 @@ template <int ROUNDS> struct SortSmem {
     static constexpr int kSlots = (kItems * 4 / 3 + 15) / 16 * 16;
     static constexpr uint32_t kDummySlot = kItems;               // p slot of the null items
     LevelTable lt;
-    int win_x[kSortLevels], win_y[kSortLevels];                  // window origin of each level, this tile
     int stat[kSortLevels][4];                                    // sum x0, sum y0, points in range (this tile)
     uint32_t warp_tot[8];
     uint32_t n_runs, n_win_loose, n_overflow, pad_;
@@ -247,11 +245,6 @@ msda_bwd_sorted(const VT *__restrict__ grad_out, const VT *__restrict__ value, c
             const uint32_t in_y = ((unsigned)uy < (unsigned)kWinY ? 3u : 0u) | ((unsigned)(uy + 1) < (unsigned)kWinY ? 12u : 0u);
             const uint32_t inw = in_x & in_y & (uint32_t)sp[r].valid;
             mask[r] = inw | (((uint32_t)sp[r].valid & ~inw) << 4);
-        }
-        if (tid < d.L) {      // the same origins, published for the scan
-            const int4 st = *reinterpret_cast<const int4 *>(sm.stat[tid]);
-            sm.win_x[tid] = window_origin(st.x, st.z, kWinX, lt.W[tid]);
-            sm.win_y[tid] = window_origin(st.y, st.z, kWinY, lt.H[tid]);
         }
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
